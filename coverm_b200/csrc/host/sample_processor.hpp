@@ -1,0 +1,441 @@
+// One BAM file ("stoit") through the device library: decode -> pinned SoA batches -> cmb_submit_batch -> per-contig
+// integer statistics.  This is the record loop of contig.rs:107-215 / genome.rs:109-227, 516-729 with the CIGAR walk
+// and the filters moved onto the GPU; the host keeps only what needs read names (mate matching, filter.rs:149-224).
+#pragma once
+#include <chrono>
+#include <cstdio>
+
+#include "bam_source.hpp"
+
+namespace cmbh {
+
+inline double now_s() {
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+inline std::string file_stem(const std::string& path) {  // Path::file_stem (bam_generator.rs:360-365)
+  size_t s = path.find_last_of('/');
+  std::string base = s == std::string::npos ? path : path.substr(s + 1);
+  size_t d = base.find_last_of('.');
+  if (d == std::string::npos || d == 0) return base;
+  return base.substr(0, d);
+}
+
+struct SampleTiming {
+  double total_s = 0, decode_s = 0, submit_wait_s = 0, end_sample_s = 0;
+  cmb_sample_timing device{};
+};
+
+struct SampleResult {
+  std::string stoit_name;
+  Header header;
+  std::vector<cmb_contig_stats> rows;
+  std::vector<cmb_hist_pair> pairs;
+  uint64_t num_detected_primary_alignments = 0;  // bam_generator.rs:113-119 / filter.rs:94-96,129-131
+  uint64_t n_records = 0;                        // every record read from the file
+  SampleTiming timing;
+};
+
+[[noreturn]] inline void throw_device_error(cmb_ctx* ctx, int rc) {
+  const std::string msg = cmb_last_error(ctx);
+  if (rc == CMB_E_UNSORTED || rc == CMB_E_NM || rc == CMB_E_BOUNDS) throw Panic(msg);
+  throw ExitError(1, "device error " + std::to_string(rc) + ": " + msg);
+}
+
+// Converts SAM text to BAM record bytes so that one decoder serves both (htslib reads SAM through the same
+// bam::Reader; tests/data/mapq_test.sam).  Integer aux tags get htslib's smallest-fitting type.
+class SamToBam {
+ public:
+  static bool looks_like_sam(const uint8_t* p, size_t n) { return n == 0 || p[0] == '@' || (n > 4 && memcmp(p, "BAM\1", 4) != 0); }
+  static void convert(const uint8_t* p, size_t n, Header& header, std::vector<uint8_t>& out) {
+    std::unordered_map<std::string, int32_t> name_to_tid;
+    size_t o = 0;
+    auto next_line = [&](std::string& line) {
+      if (o >= n) return false;
+      size_t e = o;
+      while (e < n && p[e] != '\n') ++e;
+      line.assign((const char*)p + o, e - o);
+      o = e < n ? e + 1 : e;
+      if (!line.empty() && line.back() == '\r') line.pop_back();
+      return true;
+    };
+    auto split = [](const std::string& s) {
+      std::vector<std::string> v;
+      size_t a = 0;
+      for (;;) {
+        size_t b = s.find('\t', a);
+        if (b == std::string::npos) { v.push_back(s.substr(a)); break; }
+        v.push_back(s.substr(a, b - a));
+        a = b + 1;
+      }
+      return v;
+    };
+    out.assign({'B', 'A', 'M', 1});
+    std::string line;
+    std::vector<uint8_t> body;
+    auto put32 = [](std::vector<uint8_t>& v, uint32_t x) { for (int k = 0; k < 4; ++k) v.push_back((x >> (8 * k)) & 0xff); };
+    auto put16 = [](std::vector<uint8_t>& v, uint32_t x) { v.push_back(x & 0xff); v.push_back((x >> 8) & 0xff); };
+    bool header_done = false;
+    std::vector<uint8_t> recs;
+    while (next_line(line)) {
+      if (line.empty()) continue;
+      if (line[0] == '@' && !header_done) {
+        if (line.compare(0, 3, "@SQ") == 0) {
+          std::string sn;
+          uint64_t ln = 0;
+          for (auto& f : split(line)) {
+            if (f.compare(0, 3, "SN:") == 0) sn = f.substr(3);
+            if (f.compare(0, 3, "LN:") == 0) ln = strtoull(f.c_str() + 3, nullptr, 10);
+          }
+          name_to_tid[sn] = (int32_t)header.names.size();
+          header.names.push_back(sn);
+          header.lens.push_back(ln);
+        }
+        continue;
+      }
+      header_done = true;
+      auto f = split(line);
+      if (f.size() < 11) throw Panic("Error reading BAM record: malformed SAM line");
+      auto tid_of = [&](const std::string& s) -> int32_t {
+        if (s == "*") return -1;
+        auto it = name_to_tid.find(s);
+        if (it == name_to_tid.end()) throw Panic("Error reading BAM record: unknown reference " + s);
+        return it->second;
+      };
+      const int32_t tid = tid_of(f[2]);
+      std::vector<uint32_t> cigar;
+      if (f[5] != "*") {
+        const char* c = f[5].c_str();
+        while (*c) {
+          char* e;
+          const uint32_t len = (uint32_t)strtoul(c, &e, 10);
+          static const char* ops = "MIDNSHP=X";
+          const char* w = *e ? strchr(ops, *e) : nullptr;
+          if (!w) throw Panic("Error reading BAM record: bad CIGAR");
+          cigar.push_back((len << 4) | (uint32_t)(w - ops));
+          c = e + 1;
+        }
+      }
+      const uint32_t l_seq = f[9] == "*" ? 0 : (uint32_t)f[9].size();
+      body.clear();
+      put32(body, (uint32_t)tid);
+      put32(body, (uint32_t)((int32_t)strtol(f[3].c_str(), nullptr, 10) - 1));
+      body.push_back((uint8_t)std::min<size_t>(255, f[0].size() + 1));
+      body.push_back((uint8_t)strtoul(f[4].c_str(), nullptr, 10));
+      put16(body, 0);
+      put16(body, (uint32_t)cigar.size());
+      put16(body, (uint32_t)strtoul(f[1].c_str(), nullptr, 10));
+      put32(body, l_seq);
+      put32(body, (uint32_t)(f[6] == "=" ? tid : tid_of(f[6])));
+      put32(body, (uint32_t)((int32_t)strtol(f[7].c_str(), nullptr, 10) - 1));
+      put32(body, (uint32_t)strtol(f[8].c_str(), nullptr, 10));
+      body.insert(body.end(), f[0].begin(), f[0].begin() + std::min<size_t>(254, f[0].size()));
+      body.push_back(0);
+      for (uint32_t cg : cigar) put32(body, cg);
+      body.insert(body.end(), (l_seq + 1) / 2 + l_seq, 0);
+      for (size_t i = 11; i < f.size(); ++i) {
+        if (f[i].size() < 5 || f[i][2] != ':' || f[i][4] != ':') continue;
+        if (f[i][0] != 'N' || f[i][1] != 'M') continue;  // only NM matters on this path
+        body.push_back('N');
+        body.push_back('M');
+        if (f[i][3] == 'i') {
+          const long long v = strtoll(f[i].c_str() + 5, nullptr, 10);
+          if (v < 0) { body.push_back('i'); put32(body, (uint32_t)(int32_t)v); }
+          else if (v <= 0xff) { body.push_back('C'); body.push_back((uint8_t)v); }
+          else if (v <= 0xffff) { body.push_back('S'); put16(body, (uint32_t)v); }
+          else { body.push_back('I'); put32(body, (uint32_t)v); }
+        } else {
+          body.push_back('A');
+          body.push_back('?');
+        }
+      }
+      put32(recs, (uint32_t)body.size());
+      recs.insert(recs.end(), body.begin(), body.end());
+    }
+    put32(out, 0);  // l_text
+    put32(out, (uint32_t)header.names.size());
+    for (size_t i = 0; i < header.names.size(); ++i) {
+      put32(out, (uint32_t)header.names[i].size() + 1);
+      out.insert(out.end(), header.names[i].begin(), header.names[i].end());
+      out.push_back(0);
+      put32(out, (uint32_t)header.lens[i]);
+    }
+    out.insert(out.end(), recs.begin(), recs.end());
+    header = Header{};  // re-parsed from the BAM bytes by the caller
+  }
+};
+
+class DeviceSession {
+ public:
+  DeviceSession(int device, int threads, uint32_t batch_records = 1u << 20) : pool_(threads) {
+    cmb_device_cfg cfg{};
+    cfg.device = device;
+    cfg.batch_records = batch_records;
+    cfg.batch_intervals = batch_records + batch_records / 2;
+    cfg.n_staging = 3;
+    int rc = cmb_create(&cfg, &ctx_);
+    if (rc != CMB_OK) throw ExitError(1, std::string("cannot create the CUDA coverage context: ") + cmb_last_error(nullptr));
+    batch_records_ = cfg.batch_records;
+    batch_intervals_ = cfg.batch_intervals;
+  }
+  ~DeviceSession() { cmb_destroy(ctx_); }
+  DeviceSession(const DeviceSession&) = delete;
+  ThreadPool& pool() { return pool_; }
+  cmb_ctx* ctx() { return ctx_; }
+
+  // Restrict this session to the contig shard [begin, end) (multi-GPU); (0, UINT32_MAX) = everything.
+  void set_shard(uint32_t begin, uint32_t end) { shard_begin_ = begin; shard_end_ = end; ref_lens_.clear(); }
+
+  SampleResult process(const InputSpec& in, const cmb_params& params) {
+    SampleResult res;
+    const double t0 = now_s();
+    res.stoit_name = file_stem(in.path);
+    ByteSource bytes(in);
+    std::vector<uint8_t> sam_as_bam;
+    const uint8_t* p = bytes.data();
+    size_t n = bytes.size();
+    if (!(n >= 2 && p[0] == 0x1f && p[1] == 0x8b) && SamToBam::looks_like_sam(p, n)) {
+      SamToBam::convert(p, n, res.header, sam_as_bam);
+      p = sam_as_bam.data();
+      n = sam_as_bam.size();
+    }
+    InflateStream stream(p, n, pool_, 48u << 20);
+    std::vector<uint8_t> buf;
+    size_t begin = 0;  // first unconsumed byte of buf
+    auto need = [&](size_t bytes_needed) {  // make buf[begin, begin+bytes_needed) available; false at EOF
+      while (buf.size() - begin < bytes_needed) {
+        if (begin) {
+          buf.erase(buf.begin(), buf.begin() + (ptrdiff_t)begin);
+          begin = 0;
+        }
+        if (!stream.fill(buf)) return false;
+      }
+      return true;
+    };
+    // ---- header (SAMv1 §4.2)
+    if (!need(12) || memcmp(buf.data() + begin, "BAM\1", 4) != 0) throw Panic("Error reading BAM header: not a BAM/SAM file: " + in.path);
+    const uint32_t l_text = rd_u32(buf.data() + begin + 4);
+    if (!need(12 + (size_t)l_text)) throw Panic("Error reading BAM header: truncated");
+    const uint32_t n_ref = rd_u32(buf.data() + begin + 8 + l_text);
+    size_t o = 12 + (size_t)l_text;
+    res.header.names.reserve(n_ref);
+    res.header.lens.reserve(n_ref);
+    for (uint32_t i = 0; i < n_ref; ++i) {
+      if (!need(o + 4)) throw Panic("Error reading BAM header: truncated");
+      const uint32_t l_name = rd_u32(buf.data() + begin + o);
+      if (!need(o + 8 + l_name)) throw Panic("Error reading BAM header: truncated");
+      res.header.names.emplace_back((const char*)buf.data() + begin + o + 4, l_name ? l_name - 1 : 0);
+      res.header.lens.push_back(rd_u32(buf.data() + begin + o + 4 + l_name));
+      o += 8 + l_name;
+    }
+    begin += o;
+
+    // ---- device reference + params
+    int rc;
+    const uint32_t sb = std::min<uint32_t>(shard_begin_, n_ref), se = std::min<uint32_t>(shard_end_, n_ref);
+    if (res.header.lens != ref_lens_) {
+      rc = cmb_set_reference(ctx_, n_ref, res.header.lens.data(), sb, se);
+      if (rc) throw_device_error(ctx_, rc);
+      ref_lens_ = res.header.lens;
+    }
+    cmb_filter_mode mode{};
+    rc = cmb_set_params(ctx_, &params, &mode);
+    if (rc) throw_device_error(ctx_, rc);
+    rc = cmb_begin_sample(ctx_);
+    if (rc) throw_device_error(ctx_, rc);
+
+    // ---- records
+    cmb_read_batch batch{};
+    bool have_batch = false;
+    uint32_t used_r = 0, used_i = 0;
+    double wait_s = 0;
+    auto acquire = [&]() {
+      const double a = now_s();
+      int r2 = cmb_acquire_batch(ctx_, &batch);
+      wait_s += now_s() - a;
+      if (r2) throw_device_error(ctx_, r2);
+      have_batch = true;
+      used_r = used_i = 0;
+    };
+    auto submit = [&]() {
+      if (!have_batch) return;
+      batch.iv_begin[used_r] = used_i;
+      const double a = now_s();
+      int r2 = cmb_submit_batch(ctx_, used_r, used_i);
+      wait_s += now_s() - a;
+      if (r2) throw_device_error(ctx_, r2);
+      have_batch = false;
+    };
+    const bool pair_mode = mode.filter_pairs;
+    std::vector<size_t> rec_off;
+    constexpr size_t ITEM = 4096;  // records per parallel work item
+    struct ItemOut {
+      std::vector<int32_t> iv_start, iv_len;
+      uint64_t primaries = 0;
+    };
+    std::vector<ItemOut> items;
+    std::vector<Tuple> tuples;  // pair mode only
+    // mate matching state (filter.rs:16-18)
+    struct Stored {
+      Tuple t;
+      std::vector<int32_t> iv_start, iv_len;
+    };
+    std::map<std::string, Stored> first_set;
+    int32_t current_reference = -1;
+
+    auto put_record = [&](const Tuple& t, const int32_t* ivs, const int32_t* ivl) {
+      const uint32_t i = used_r++;
+      batch.tid[i] = t.tid; batch.pos[i] = t.pos; batch.flag[i] = t.flag; batch.mapq[i] = t.mapq;
+      batch.nm_state[i] = t.nm_state; batch.nm[i] = t.nm; batch.l_seq[i] = t.l_seq; batch.aligned[i] = t.aligned;
+      batch.del[i] = t.del; batch.ins[i] = t.ins; batch.iv_begin[i] = used_i;
+      for (uint32_t k = 0; k < t.n_iv; ++k) {
+        batch.iv_start[used_i] = ivs[k];
+        batch.iv_len[used_i] = ivl[k];
+        ++used_i;
+      }
+    };
+
+    for (;;) {
+      // complete records currently in buf
+      rec_off.clear();
+      size_t q = begin;
+      size_t max_iv = 0;
+      while (q + 4 <= buf.size()) {
+        const uint32_t bs = rd_u32(buf.data() + q);
+        if (bs < 32) throw Panic("Error reading BAM record: corrupt block_size");
+        if (q + 4 + (size_t)bs > buf.size()) break;
+        rec_off.push_back(q);
+        max_iv += rd_u16(buf.data() + q + 4 + 12);
+        q += 4 + (size_t)bs;
+        if (rec_off.size() == batch_records_ / 2) break;  // keep one window within a batch
+      }
+      if (rec_off.empty()) {
+        if (!need((buf.size() - begin) + 1)) break;  // EOF
+        continue;
+      }
+      const size_t nrec = rec_off.size();
+      res.n_records += nrec;
+      const size_t n_items = (nrec + ITEM - 1) / ITEM;
+      if (items.size() < n_items) items.resize(n_items);
+      if (max_iv > batch_intervals_) throw ExitError(1, "a window of records has more aligned blocks than a device batch holds");
+
+      if (!pair_mode) {
+        if (have_batch && (used_r + nrec > batch_records_ || used_i + max_iv > batch_intervals_)) submit();
+        if (!have_batch) acquire();
+        const uint32_t r_base = used_r;
+        const uint8_t* base = buf.data();
+        pool_.parallel_for(n_items, [&](size_t it, int) {
+          ItemOut& io = items[it];
+          io.iv_start.clear();
+          io.iv_len.clear();
+          io.primaries = 0;
+          const size_t r0 = it * ITEM, r1 = std::min(nrec, r0 + ITEM);
+          Tuple t;
+          for (size_t r = r0; r < r1; ++r) {
+            const uint32_t before = (uint32_t)io.iv_start.size();
+            decode_bam_record(base + rec_off[r], t, io.iv_start, io.iv_len);
+            const uint32_t i = r_base + (uint32_t)r;
+            batch.tid[i] = t.tid; batch.pos[i] = t.pos; batch.flag[i] = t.flag; batch.mapq[i] = t.mapq;
+            batch.nm_state[i] = t.nm_state; batch.nm[i] = t.nm; batch.l_seq[i] = t.l_seq; batch.aligned[i] = t.aligned;
+            batch.del[i] = t.del; batch.ins[i] = t.ins;
+            batch.iv_begin[i] = before;  // item-local; rebased below
+            if (!(t.flag & 0x900)) ++io.primaries;
+          }
+        });
+        // rebase interval offsets (items are in record order)
+        std::vector<uint32_t> item_base(n_items);
+        uint32_t acc = used_i;
+        for (size_t it = 0; it < n_items; ++it) {
+          item_base[it] = acc;
+          acc += (uint32_t)items[it].iv_start.size();
+          res.num_detected_primary_alignments += items[it].primaries;
+        }
+        pool_.parallel_for(n_items, [&](size_t it, int) {
+          const ItemOut& io = items[it];
+          const size_t r0 = it * ITEM, r1 = std::min(nrec, r0 + ITEM);
+          for (size_t r = r0; r < r1; ++r) batch.iv_begin[r_base + r] += item_base[it];
+          if (!io.iv_start.empty()) {
+            memcpy(batch.iv_start + item_base[it], io.iv_start.data(), 4 * io.iv_start.size());
+            memcpy(batch.iv_len + item_base[it], io.iv_len.data(), 4 * io.iv_len.size());
+          }
+        });
+        used_r += (uint32_t)nrec;
+        used_i = acc;
+      } else {
+        // filter.rs:117-233: decode in parallel, then match mates in stream order; only completed pairs reach the GPU
+        tuples.resize(nrec);
+        std::vector<uint32_t> iv_at(nrec);
+        const uint8_t* base = buf.data();
+        pool_.parallel_for(n_items, [&](size_t it, int) {
+          ItemOut& io = items[it];
+          io.iv_start.clear();
+          io.iv_len.clear();
+          const size_t r0 = it * ITEM, r1 = std::min(nrec, r0 + ITEM);
+          for (size_t r = r0; r < r1; ++r) {
+            iv_at[r] = (uint32_t)io.iv_start.size();
+            decode_bam_record(base + rec_off[r], tuples[r], io.iv_start, io.iv_len);
+          }
+        });
+        for (size_t r = 0; r < nrec; ++r) {
+          const Tuple& t = tuples[r];
+          const ItemOut& io = items[r / ITEM];
+          const int32_t* ivs = io.iv_start.data() + iv_at[r];
+          const int32_t* ivl = io.iv_len.data() + iv_at[r];
+          if (!(t.flag & 0x900)) res.num_detected_primary_alignments += 1;
+          if (t.flag & 0x900) continue;   // secondary / supplementary (filter.rs:138-140)
+          if (!(t.flag & 0x2)) continue;  // not a proper pair (filter.rs:141-147, filter_out = true)
+          if (t.tid != current_reference) {
+            current_reference = t.tid;
+            first_set.clear();
+          }
+          std::string qname = bam_qname(base + rec_off[r]);
+          auto itf = first_set.find(qname);
+          if (itf == first_set.end()) {
+            if (t.mtid == current_reference) {
+              Stored s;
+              s.t = t;
+              s.iv_start.assign(ivs, ivs + t.n_iv);
+              s.iv_len.assign(ivl, ivl + t.n_iv);
+              first_set.emplace(std::move(qname), std::move(s));
+            }
+          } else {
+            const Stored& s = itf->second;
+            if (have_batch && (used_r + 2 > batch_records_ || used_i + s.t.n_iv + t.n_iv > batch_intervals_)) submit();
+            if (!have_batch) acquire();
+            put_record(s.t, s.iv_start.data(), s.iv_len.data());  // stored first mate at the even index
+            put_record(t, ivs, ivl);
+            first_set.erase(itf);
+          }
+        }
+      }
+      begin = q;
+    }
+    const double t_dec = now_s();
+    submit();
+    res.rows.resize(n_ref);
+    uint64_t n_pairs = 0;
+    rc = cmb_end_sample(ctx_, res.rows.data(), nullptr, 0, &n_pairs);
+    if (rc) throw_device_error(ctx_, rc);
+    if ((params.want & CMB_WANT_HIST_CSR) && n_pairs) {
+      res.pairs.resize(n_pairs);
+      rc = cmb_fetch_pairs(ctx_, res.pairs.data(), n_pairs);
+      if (rc) throw_device_error(ctx_, rc);
+    }
+    cmb_get_timing(ctx_, &res.timing.device);
+    const double t1 = now_s();
+    res.timing.total_s = t1 - t0;
+    res.timing.decode_s = t_dec - t0 - wait_s;
+    res.timing.submit_wait_s = wait_s;
+    res.timing.end_sample_s = t1 - t_dec;
+    return res;
+  }
+
+ private:
+  ThreadPool pool_;
+  cmb_ctx* ctx_ = nullptr;
+  uint32_t batch_records_ = 0, batch_intervals_ = 0;
+  uint32_t shard_begin_ = 0, shard_end_ = 0xffffffffu;
+  std::vector<uint64_t> ref_lens_;
+};
+
+}  // namespace cmbh

@@ -1,0 +1,205 @@
+/*
+ * coverm_b200.h — C ABI of libcoverm_b200.so: the B200 (sm_100a) replacement for
+ * CoverM's per-contig coverage hot path.
+ *
+ * All citations are file:line under the reference tree (wwood/CoverM v0.8.0).
+ *
+ * Where it plugs in.  The reference's hot path is the body of the record loop
+ * plus the per-contig flush of its three drivers:
+ *     contig_coverage()                              src/contig.rs:13-253
+ *     mosdepth_genome_coverage_with_contig_names()   src/genome.rs:17-322
+ *     mosdepth_genome_coverage()                     src/genome.rs:419-797
+ * i.e.  NamedBamReader::read (bam_generator.rs:21-38)
+ *         -> [ReferenceSortedBamFilter::read  filter.rs:86-234]  -> FlagFilter::passes (lib.rs:59-79)
+ *         -> CIGAR walk into `ups_and_downs: Vec<i32>` (contig.rs:166-202)
+ *         -> MosdepthGenomeCoverageEstimator::add_contig(&[i32], reads, mismatches, identity)
+ *            (mosdepth_genome_coverage_estimators.rs:366-528, "EST")
+ *         -> calculate_coverage (EST:530-839) -> CoverageTaker (coverage_takers.rs:29-38).
+ * add_contig takes a dense host array per contig, so the device boundary sits
+ * one level up: the host reduces each BAM record to a fixed tuple (+ its
+ * M/=/X intervals), this library does filter + delta accumulation + prefix sum
+ * + every O(contig length) reduction on the GPU, and hands back per-contig
+ * INTEGER sufficient statistics from which the host replays calculate_coverage
+ * verbatim in f32/f64.  A Rust host binds these symbols from the same spot in
+ * contig.rs / genome.rs.
+ *
+ * Conventions: every function returns 0 on success or a negative CMB_E_* code
+ * (never throws / aborts across the ABI); cmb_last_error() gives the message.
+ * The caller owns every host result buffer; the library owns the pinned
+ * staging buffers and all device memory.  One cmb_ctx per (GPU, host thread);
+ * a ctx is not thread-safe.  There is NO CPU fallback: cmb_create fails if no
+ * CUDA device is usable.
+ */
+#ifndef COVERM_B200_H
+#define COVERM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMB_ABI_VERSION 1
+
+/* error codes */
+#define CMB_OK 0
+#define CMB_E_CUDA (-1)      /* CUDA runtime / driver failure                               */
+#define CMB_E_ARG (-2)       /* bad argument / call order                                   */
+#define CMB_E_NOMEM (-3)     /* device or pinned allocation failed                          */
+#define CMB_E_UNSORTED (-4)  /* records not sorted by reference   (contig.rs:129-132 panic) */
+#define CMB_E_NM (-5)        /* NM aux missing / wrong type where the reference calls nm()  (lib.rs:138-158 panic) */
+#define CMB_E_BOUNDS (-6)    /* an aligned block starts at/after the contig end (contig.rs:178 index panic) */
+#define CMB_E_CAPACITY (-7)  /* a device-side buffer (histogram records) overflowed         */
+
+typedef struct cmb_ctx cmb_ctx;
+
+typedef struct cmb_device_cfg {
+  int32_t device;             /* CUDA device ordinal                                         */
+  uint32_t batch_records;     /* capacity (records) of each pinned staging batch            */
+  uint32_t batch_intervals;   /* capacity (intervals) of each pinned staging batch          */
+  uint32_t n_staging;         /* number of staging batches (>= 2: decode overlaps H2D + K1) */
+} cmb_device_cfg;
+
+/* Which statistics the host needs (selects kernel variants). */
+#define CMB_WANT_HIST 1u      /* depth histogram of the end-trimmed window: trimmed_mean / variance /
+                                 coverage_histogram (EST:410-466)                                     */
+#define CMB_WANT_HIST_CSR 2u  /* also return the merged per-contig histogram as (depth,count) pairs  */
+
+/* Filter / estimator parameters: FlagFilter (lib.rs:59-64), ReferenceSortedBamFilter::new
+ * arguments (filter.rs:36-47), FilterParameters::doing_filtering (coverm.rs:1695-1703),
+ * contig_end_exclusion / trim bounds (coverm.rs:1317-1318, 1364-1372). */
+typedef struct cmb_params {
+  uint8_t include_improper_pairs;
+  uint8_t include_supplementary;
+  uint8_t include_secondary;
+  uint8_t filtering;                 /* 1: a ReferenceSortedBamFilter (filter_out = true) precedes the flag filter */
+  uint8_t min_mapq;                  /* 255 = no MAPQ filtering (filter.rs:13)                  */
+  uint8_t reserved0[3];
+  uint32_t min_aligned_length_single;
+  float min_percent_identity_single;
+  float min_aligned_percent_single;
+  uint32_t min_aligned_length_pair;
+  float min_percent_identity_pair;
+  float min_aligned_percent_pair;
+  uint64_t contig_end_exclusion;     /* E: the window of a contig of length L is [E, L-E) when 2E < L */
+  float trim_min;                    /* trimmed-mean bounds as fractions (EST:591-592)          */
+  float trim_max;
+  uint32_t want;                     /* CMB_WANT_* bitmask                                      */
+  uint32_t reserved1;
+} cmb_params;
+
+/* Derived filter gating (filter.rs:48-61), filled by cmb_set_params for the host:
+ * when filter_pairs is set the host must perform mate matching (filter.rs:149-184)
+ * and submit only completed pairs, first mate at an even index, second right after. */
+typedef struct cmb_filter_mode {
+  uint8_t filter_single_reads;
+  uint8_t filter_pairs;
+} cmb_filter_mode;
+
+/* One staging batch, SoA.  Pointers are into pinned host memory owned by the ctx;
+ * valid from cmb_acquire_batch until the matching cmb_submit_batch.
+ * Record i covers intervals [iv_begin[i], iv_begin[i+1]) — the host writes
+ * iv_begin[n_records] = n_intervals.  39 B per record + 8 B per interval. */
+typedef struct cmb_read_batch {
+  uint32_t capacity_records;
+  uint32_t capacity_intervals;
+  int32_t* tid;       /* record.tid()                                   contig.rs:124 */
+  int32_t* pos;       /* record.pos(), 0-based leftmost                  contig.rs:166 */
+  uint16_t* flag;     /* BAM FLAG                                        lib.rs:67-78  */
+  uint8_t* mapq;      /*                                                 filter.rs:251 */
+  uint8_t* nm_state;  /* 1: NM aux present with type C/S/I; 0: absent; 2: other type (lib.rs:139-156) */
+  uint32_t* nm;       /* NM value                                                       */
+  uint32_t* l_seq;    /* record.seq().len()                              filter.rs:277 */
+  uint32_t* aligned;  /* sum len(M,I,D,=,X)            filter.rs:261, contig.rs:171-199 */
+  uint32_t* del;      /* sum len(D)  (pair filter omits D, filter.rs:304; indels contig.rs:189) */
+  uint32_t* ins;      /* sum len(I)                                      contig.rs:197 */
+  uint32_t* iv_begin; /* capacity_records + 1 entries                                   */
+  int32_t* iv_start;  /* 0-based reference start of each M/=/X block     contig.rs:178 */
+  int32_t* iv_len;    /* its length                                      contig.rs:179 */
+} cmb_read_batch;
+
+/* Per-contig integer sufficient statistics (one row per reference sequence). */
+typedef struct cmb_contig_stats {
+  uint64_t n_records;            /* records that survived every filter and are mapped here; "seen" iff > 0
+                                    (contig.rs:125-155); names-mode read count (genome.rs:173-174)         */
+  uint64_t n_primary;            /* ... and neither secondary nor supplementary   (contig.rs:157-159)      */
+  uint64_t n_nonsupp;            /* ... and not supplementary                     (genome.rs:677-682)      */
+  uint64_t sum_edit;             /* sum of NM                                     (contig.rs:206-207)      */
+  uint64_t sum_indel;            /* sum of I+D lengths                            (contig.rs:189,197)      */
+  double sum_identity_primary;   /* sum (aligned-NM)/aligned over primaries       (contig.rs:208-211)      */
+  double sum_identity_nonsupp;   /* same over non-supplementary records           (genome.rs:220-223)      */
+  uint64_t sum_depth_window;     /* sum of depth over the window                  (EST:402)                */
+  uint64_t covered_window;       /* window bases with depth > 0                   (EST:399-401, 457-459)   */
+  uint64_t covered_full;         /* all bases with depth > 0 (no end exclusion)   (EST:496-501)            */
+  /* histogram-derived, valid with CMB_WANT_HIST; contig mode semantics (unobserved = [0], contig.rs:65): */
+  uint64_t trimmed_total;        /* `total` of the trimmed-mean walk              (EST:598-642)            */
+  uint64_t trim_min_index;       /* floor(trim_min * T as f32)                    (EST:591)                */
+  uint64_t trim_max_index;       /* ceil(trim_max * T as f32)                     (EST:592)                */
+  uint64_t var_k;                /* lowest depth with a non-zero count            (EST:790-795)            */
+  uint64_t var_ex;               /* sum (x-k) n_x      (wrapping u64)             (EST:796-805)            */
+  uint64_t var_ex2;              /* sum (x-k)^2 n_x    (wrapping u64)                                      */
+  uint64_t hist_offset;          /* CMB_WANT_HIST_CSR: first pair of this contig in the pair array         */
+  uint32_t hist_count;           /* number of (depth,count) pairs, ascending depth                         */
+  uint32_t reserved;
+} cmb_contig_stats;
+
+typedef struct cmb_hist_pair {
+  uint32_t depth;
+  uint32_t count;
+} cmb_hist_pair;
+
+/* Timings of the last sample, measured with CUDA events on the ctx stream. */
+typedef struct cmb_sample_timing {
+  float ms_zero;      /* K0: arena + row zero fill                     */
+  float ms_accumulate;/* K1 launches (sum over batches, incl. H2D waits on the stream) */
+  float ms_scan;      /* K2: segmented scan + reductions + histogram emit */
+  float ms_finalize;  /* K3: per-contig histogram merge + trimmed/variance walk */
+  float ms_total;     /* begin_sample .. end_sample on the stream      */
+  uint64_t arena_elems;   /* padded i32 elements scanned by K2        */
+  uint64_t n_records;     /* records submitted                         */
+  uint64_t n_intervals;   /* intervals submitted                       */
+  uint32_t k1_launches, k2_launches, k3_launches, reserved;
+} cmb_sample_timing;
+
+int cmb_abi_version(void);
+
+/* Create / destroy a context on one GPU. */
+int cmb_create(const cmb_device_cfg* cfg, cmb_ctx** out);
+void cmb_destroy(cmb_ctx* ctx);
+const char* cmb_last_error(const cmb_ctx* ctx); /* ctx may be NULL: last cmb_create error */
+
+/* Reference layout: `vec![0; header.target_len(tid)]` for every tid at once
+ * (contig.rs:144-145).  [tid_begin, tid_end) is the shard this context owns
+ * (multi-GPU contig sharding); records on other tids are ignored. */
+int cmb_set_reference(cmb_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, uint32_t tid_begin,
+                      uint32_t tid_end);
+int cmb_set_params(cmb_ctx* ctx, const cmb_params* params, cmb_filter_mode* mode_out);
+
+/* One BAM file ("stoit", contig.rs:22-27). */
+int cmb_begin_sample(cmb_ctx* ctx);
+int cmb_acquire_batch(cmb_ctx* ctx, cmb_read_batch* batch);                       /* blocks until a staging batch is free */
+int cmb_submit_batch(cmb_ctx* ctx, uint32_t n_records, uint32_t n_intervals);     /* async: H2D + filter/delta kernel      */
+/* Device-resident input variant (all pointers are DEVICE pointers laid out as cmb_read_batch;
+ * used for device-only timing and by hosts that already stage tuples in HBM). */
+int cmb_submit_device_batch(cmb_ctx* ctx, const cmb_read_batch* dev_batch, uint32_t n_records, uint32_t n_intervals);
+/* Scan + reduce + copy back.  `stats` has n_contigs rows (rows outside the shard are zeroed).
+ * `pairs`/`pairs_capacity` receive the CSR histogram when CMB_WANT_HIST_CSR is set (may be NULL otherwise);
+ * *n_pairs gets the number of pairs produced. */
+int cmb_end_sample(cmb_ctx* ctx, cmb_contig_stats* stats, cmb_hist_pair* pairs, uint64_t pairs_capacity,
+                   uint64_t* n_pairs);
+/* Copies the CSR histogram pairs of the sample just ended (CMB_WANT_HIST_CSR) into `pairs`
+ * (call cmb_end_sample with pairs == NULL first to learn *n_pairs). */
+int cmb_fetch_pairs(cmb_ctx* ctx, cmb_hist_pair* pairs, uint64_t n_pairs);
+/* Same, but leaves the rows in device memory (no D2H): *dev_stats is a device pointer to n_contigs rows,
+ * valid until the next cmb_begin_sample.  For device-only timing and for NCCL all-gather by the caller. */
+int cmb_end_sample_device(cmb_ctx* ctx, const cmb_contig_stats** dev_stats);
+
+int cmb_get_timing(const cmb_ctx* ctx, cmb_sample_timing* out);
+/* cudaStream_t of the context (as void*), for callers that order their own work after it. */
+void* cmb_stream(cmb_ctx* ctx);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* COVERM_B200_H */

@@ -1,0 +1,69 @@
+/*
+ * coverm_b200_host.h — C ABI of the host half of libcoverm_b200.so: the `coverm contig` / `coverm genome`
+ * (--bam-files) drivers built on the device ABI of coverm_b200.h.  This is the call a non-Rust embedder makes;
+ * it corresponds to run_contig / run_genome in the reference (src/bin/coverm.rs:2088-2131, 1539-1628), i.e.
+ * contig_coverage (src/contig.rs:13-253) / mosdepth_genome_coverage* (src/genome.rs:17-322, 419-797) followed by
+ * CoveragePrinter::finalise_printing (src/coverage_printer.rs:20-121).
+ *
+ * argv is the coverm command line without the program name, e.g.
+ *   {"contig", "-m", "mean", "trimmed_mean", "covered_fraction", "-b", "sample.bam", "-t", "32"}
+ * BAM inputs may be given as host memory buffers (`mem`): a `-b` path equal to mem[i].path is read from
+ * mem[i].data instead of the filesystem.  The table is returned as text exactly as the reference prints it.
+ */
+#ifndef COVERM_B200_HOST_H
+#define COVERM_B200_HOST_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CMBH_MAX_SAMPLES 64
+
+typedef struct cmbh_mem_input {
+  const char* path;
+  const uint8_t* data;
+  size_t size;
+} cmbh_mem_input;
+
+typedef struct cmbh_sample_info {
+  uint64_t num_mapped_reads; /* ReadsMapped (src/lib.rs:53-57) */
+  uint64_t num_reads;
+  uint64_t n_records;        /* records read from the file */
+  double total_s, decode_s, submit_wait_s, end_sample_s;
+  float k0_ms, k1_ms, k2_ms, k3_ms, device_total_ms;
+  uint32_t k1_launches, k2_launches, k3_launches;
+  uint64_t arena_elems, n_intervals;
+} cmbh_sample_info;
+
+typedef struct cmbh_result {
+  int32_t status;        /* process exit status the reference would give: 0, 1 (error!+exit), 2 (usage), 101 (panic) */
+  char* out;             /* stdout text (malloc'd; free with cmbh_free_result) */
+  size_t out_len;
+  char* err;             /* stderr text */
+  size_t err_len;
+  uint32_t n_samples;
+  cmbh_sample_info samples[CMBH_MAX_SAMPLES];
+} cmbh_result;
+
+typedef struct cmbh_session cmbh_session;
+
+/* A session owns one GPU context (pinned staging + device arena) and a host thread pool; reuse it across runs. */
+int cmbh_session_create(int device, int threads, cmbh_session** out);
+void cmbh_session_destroy(cmbh_session* s);
+const char* cmbh_last_error(void);
+/* Restrict the session to contigs [tid_begin, tid_end) (multi-GPU contig sharding); rows outside come back zero. */
+int cmbh_session_set_shard(cmbh_session* s, uint32_t tid_begin, uint32_t tid_end);
+
+int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_input* mem, int n_mem, cmbh_result* res);
+void cmbh_free_result(cmbh_result* res);
+
+/* The command-line entry point (what the `coverm` binary calls). */
+int cmbh_main(int argc, char** argv);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,270 @@
+// TEST INFRASTRUCTURE ONLY — never linked into libcoverm_b200.so or the `coverm` product binary.
+//
+// A plain-C++ stand-in for the device half of include/coverm_b200.h, so that the product's HOST code (BGZF/BAM
+// decode, batching, mate matching, driver replay, estimator finalisation, printers, CLI) can be checked against the
+// reference's golden vectors in the GPU-less build container (`oracle/coverm_hostcheck`, tests/test_host_golden.py).
+// It follows the same reference rules as the oracle (contig.rs:166-211, filter.rs:243-336, lib.rs:59-79,
+// EST:366-502, 591-642, 790-805) with dense per-contig arrays; the CUDA kernels are validated separately, on the
+// GPU, against the oracle through the real library.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../include/coverm_b200.h"
+
+struct cmb_ctx {
+  std::string err;
+  cmb_device_cfg cfg{};
+  std::vector<std::vector<uint8_t>> slabs;
+  std::vector<cmb_read_batch> batches;
+  int acquired = -1;
+  uint32_t next = 0;
+  std::vector<uint64_t> lens;
+  uint32_t tid_begin = 0, tid_end = 0;
+  cmb_params p{};
+  cmb_filter_mode mode{};
+  bool in_sample = false, ended = false;
+  std::map<uint32_t, std::vector<int32_t>> arena;
+  std::vector<cmb_contig_stats> rows;
+  std::vector<cmb_hist_pair> pairs;
+  int64_t last_kept_tid = INT64_MIN;
+  int error = 0;
+  uint64_t n_records = 0, n_intervals = 0;
+};
+
+static std::string g_err;
+static int fail(cmb_ctx* c, int code, const std::string& m) {
+  if (c) c->err = m;
+  else g_err = m;
+  return code;
+}
+
+extern "C" {
+
+int cmb_abi_version(void) { return CMB_ABI_VERSION; }
+const char* cmb_last_error(const cmb_ctx* c) { return c ? c->err.c_str() : g_err.c_str(); }
+
+int cmb_create(const cmb_device_cfg* cfg, cmb_ctx** out) {
+  cmb_ctx* c = new cmb_ctx();
+  c->cfg = *cfg;
+  if (!c->cfg.batch_records) c->cfg.batch_records = 1 << 16;
+  if (!c->cfg.batch_intervals) c->cfg.batch_intervals = c->cfg.batch_records * 2;
+  if (c->cfg.n_staging < 2) c->cfg.n_staging = 2;
+  const size_t nr = c->cfg.batch_records, ni = c->cfg.batch_intervals;
+  for (uint32_t i = 0; i < c->cfg.n_staging; ++i) {
+    c->slabs.emplace_back(4 * nr * 7 + 4 * (nr + 1) + 8 * ni + 4 * nr + 64);
+    uint8_t* p = c->slabs.back().data();
+    cmb_read_batch b{};
+    b.capacity_records = (uint32_t)nr;
+    b.capacity_intervals = (uint32_t)ni;
+    auto take = [&](size_t bytes) { uint8_t* r = p; p += bytes; return r; };
+    b.tid = (int32_t*)take(4 * nr); b.pos = (int32_t*)take(4 * nr); b.nm = (uint32_t*)take(4 * nr);
+    b.l_seq = (uint32_t*)take(4 * nr); b.aligned = (uint32_t*)take(4 * nr); b.del = (uint32_t*)take(4 * nr);
+    b.ins = (uint32_t*)take(4 * nr); b.iv_begin = (uint32_t*)take(4 * (nr + 1)); b.iv_start = (int32_t*)take(4 * ni);
+    b.iv_len = (int32_t*)take(4 * ni); b.flag = (uint16_t*)take(2 * nr); b.mapq = (uint8_t*)take(nr); b.nm_state = (uint8_t*)take(nr);
+    c->batches.push_back(b);
+  }
+  *out = c;
+  return CMB_OK;
+}
+void cmb_destroy(cmb_ctx* c) { delete c; }
+
+int cmb_set_reference(cmb_ctx* c, uint32_t n, const uint64_t* len, uint32_t b, uint32_t e) {
+  c->lens.assign(len, len + n);
+  c->tid_begin = b;
+  c->tid_end = e;
+  return CMB_OK;
+}
+
+int cmb_set_params(cmb_ctx* c, const cmb_params* p, cmb_filter_mode* mode_out) {
+  c->p = *p;
+  const bool si = p->min_aligned_length_single > 0 || p->min_percent_identity_single > 0.0f || p->min_aligned_percent_single > 0.0f;
+  const bool pi = p->min_aligned_length_pair > 0 || p->min_percent_identity_pair > 0.0f || p->min_aligned_percent_pair > 0.0f;
+  const bool fs = si || (!pi && p->min_mapq != 255);
+  const bool fp = pi || ((!fs || !p->include_improper_pairs) && p->min_mapq != 255);
+  c->mode.filter_single_reads = p->filtering ? fs : 0;
+  c->mode.filter_pairs = p->filtering ? fp : 0;
+  if (mode_out) *mode_out = c->mode;
+  return CMB_OK;
+}
+
+int cmb_begin_sample(cmb_ctx* c) {
+  c->arena.clear();
+  c->rows.assign(c->lens.size(), cmb_contig_stats{});
+  c->pairs.clear();
+  c->last_kept_tid = INT64_MIN;
+  c->error = 0;
+  c->in_sample = true;
+  c->ended = false;
+  c->n_records = c->n_intervals = 0;
+  return CMB_OK;
+}
+int cmb_acquire_batch(cmb_ctx* c, cmb_read_batch* b) {
+  *b = c->batches[c->next];
+  c->acquired = (int)c->next;
+  return CMB_OK;
+}
+
+struct Rec { uint32_t flag, mapq, nm_state, nm, l_seq, aligned, del; };
+static bool single_ok(const Rec& r, const cmb_params& p, bool* nm_err) {
+  if (p.min_mapq != 255 && (r.mapq < p.min_mapq || r.mapq == 255)) return false;
+  if (r.nm_state != 1) *nm_err = true;
+  return r.aligned >= p.min_aligned_length_single && (float)r.aligned / (float)r.l_seq >= p.min_aligned_percent_single &&
+         1.0f - (float)r.nm / (float)r.aligned >= p.min_percent_identity_single;
+}
+static bool pair_ok(const Rec& a, const Rec& b, const cmb_params& p, bool* nm_err) {
+  if (p.min_mapq != 255 && (a.mapq < p.min_mapq || b.mapq < p.min_mapq || a.mapq == 255 || b.mapq == 255)) return false;
+  if (a.nm_state != 1 || b.nm_state != 1) *nm_err = true;
+  const uint32_t al = (a.aligned - a.del) + (b.aligned - b.del);
+  return al >= p.min_aligned_length_pair && (float)al / (float)((uint64_t)a.l_seq + b.l_seq) >= p.min_aligned_percent_pair &&
+         1.0f - ((float)((uint64_t)a.nm + b.nm) / (float)al) >= p.min_percent_identity_pair;
+}
+
+static int submit(cmb_ctx* c, const cmb_read_batch& b, uint32_t n, uint32_t ni) {
+  const cmb_params& p = c->p;
+  auto rec = [&](uint32_t i) { return Rec{b.flag[i], b.mapq[i], b.nm_state[i], b.nm[i], b.l_seq[i], b.aligned[i], b.del[i]}; };
+  for (uint32_t i = 0; i < n; ++i) {
+    const Rec r = rec(i);
+    const bool unmapped = r.flag & 4, sec = r.flag & 0x100, sup = r.flag & 0x800, proper = r.flag & 2;
+    const bool flag_pass = !(sec && !p.include_secondary) && !(sup && !p.include_supplementary) && !(!proper && !p.include_improper_pairs);
+    bool keep = flag_pass && !unmapped, nm_err = false;
+    if (p.filtering) {
+      bool passes;
+      if (c->mode.filter_single_reads && !c->mode.filter_pairs) {
+        passes = !unmapped && (p.include_supplementary || !sup) && (p.include_secondary || !sec) && single_ok(r, p, &nm_err);
+      } else {
+        const uint32_t m = i ^ 1u;
+        bool ok = m < n;
+        if (ok) {
+          const Rec o = rec(m);
+          const Rec& first = (i & 1) ? o : r;
+          const Rec& second = (i & 1) ? r : o;
+          if (c->mode.filter_single_reads) ok = single_ok(first, p, &nm_err) && single_ok(second, p, &nm_err);
+          if (ok) ok = pair_ok(second, first, p, &nm_err);
+        }
+        passes = ok;
+      }
+      keep = keep && passes;
+    }
+    if (keep && r.nm_state != 1) nm_err = true;
+    if (nm_err) c->error |= 2;
+    if (!keep) continue;
+    const int32_t tid = b.tid[i];
+    if (tid < 0 || (size_t)tid >= c->lens.size()) { c->error |= 4; continue; }
+    if (tid < c->last_kept_tid) c->error |= 1;
+    c->last_kept_tid = std::max<int64_t>(c->last_kept_tid, tid);
+    if ((uint32_t)tid < c->tid_begin || (uint32_t)tid >= c->tid_end) continue;
+    cmb_contig_stats& row = c->rows[tid];
+    const bool primary = !sec && !sup;
+    row.n_records += 1;
+    row.n_primary += primary;
+    row.n_nonsupp += !sup;
+    row.sum_edit += r.nm;
+    row.sum_indel += (uint64_t)b.ins[i] + r.del;
+    if (r.aligned > 0) {
+      const double id = ((double)r.aligned - (double)r.nm) / (double)r.aligned;
+      if (primary) row.sum_identity_primary += id;
+      if (!sup) row.sum_identity_nonsupp += id;
+    }
+    auto& ud = c->arena[(uint32_t)tid];
+    if (ud.empty()) ud.assign(c->lens[tid] + 1, 0);  // +1 sentinel so a zero-length contig is still "allocated"
+    const uint64_t L = c->lens[tid];
+    for (uint32_t k = b.iv_begin[i]; k < b.iv_begin[i + 1]; ++k) {
+      const int32_t s = b.iv_start[k];
+      if (s < 0 || (uint64_t)s >= L) { c->error |= 4; continue; }
+      ud[s] += 1;
+      const uint64_t e = (uint64_t)s + (uint32_t)b.iv_len[k];
+      if (e < L) ud[e] -= 1;
+    }
+  }
+  c->n_records += n;
+  c->n_intervals += ni;
+  return CMB_OK;
+}
+
+int cmb_submit_batch(cmb_ctx* c, uint32_t n, uint32_t ni) {
+  const int i = c->acquired;
+  c->acquired = -1;
+  c->next = (uint32_t)(i + 1) % c->cfg.n_staging;
+  return submit(c, c->batches[i], n, ni);
+}
+int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* b, uint32_t n, uint32_t ni) { return submit(c, *b, n, ni); }
+
+int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** out) {
+  c->in_sample = false;
+  const uint64_t E = c->p.contig_end_exclusion;
+  const bool hist = c->p.want & (CMB_WANT_HIST | CMB_WANT_HIST_CSR), csr = c->p.want & CMB_WANT_HIST_CSR;
+  for (auto& kv : c->arena) {
+    const uint32_t tid = kv.first;
+    const uint64_t L = c->lens[tid];
+    cmb_contig_stats& row = c->rows[tid];
+    std::map<uint32_t, uint64_t> h;
+    int64_t d = 0;
+    const bool win = 2 * E < L;
+    for (uint64_t i = 0; i < L; ++i) {
+      d += kv.second[i];
+      if (d > 0) row.covered_full += 1;
+      if (win && i >= E && i < L - E) {
+        if (d > 0) row.covered_window += 1;
+        row.sum_depth_window += (uint64_t)d;
+        if (hist) h[(uint32_t)d] += 1;
+      }
+    }
+    if (!hist || !win || row.n_records == 0) continue;
+    const uint64_t T = L - 2 * E;
+    const uint64_t min_index = (uint64_t)std::floor(c->p.trim_min * (float)T), max_index = (uint64_t)std::ceil(c->p.trim_max * (float)T);
+    uint64_t cprev = 0, total = 0, s0 = 0, s1 = 0, s2 = 0, k = h.begin()->first;
+    for (auto& dc : h) {
+      const uint64_t depth = dc.first, cnt = dc.second, ccur = cprev + cnt;
+      uint64_t w;
+      if (ccur < min_index) w = 0;
+      else if (cprev < min_index) w = ccur > max_index ? max_index - min_index + 1 : ccur - min_index + 1;
+      else w = cprev > max_index ? 0 : (ccur > max_index ? max_index - cprev + 1 : cnt);
+      total += w * depth;
+      s0 += cnt; s1 += depth * cnt; s2 += depth * depth * cnt;
+      cprev = ccur;
+    }
+    row.trimmed_total = total;
+    row.trim_min_index = min_index;
+    row.trim_max_index = max_index;
+    row.var_k = k;
+    row.var_ex = s1 - k * s0;
+    row.var_ex2 = s2 - 2 * k * s1 + k * k * s0;
+    row.hist_count = (uint32_t)h.size();
+    if (csr) {
+      row.hist_offset = c->pairs.size();
+      for (auto& dc : h) c->pairs.push_back({dc.first, (uint32_t)dc.second});
+    }
+  }
+  c->ended = true;
+  if (c->error & 1) return fail(c, CMB_E_UNSORTED, "BAM file appears to be unsorted. Input BAM files must be sorted by reference (i.e. by samtools sort)");
+  if (c->error & 2) return fail(c, CMB_E_NM, "Mapping record encountered that does not have an 'NM' auxiliary tag in the SAM/BAM format. This is required to work out some coverage statistics");
+  if (c->error & 4) return fail(c, CMB_E_BOUNDS, "index out of bounds: an aligned block starts beyond the end of its reference sequence");
+  if (out) *out = c->rows.data();
+  return CMB_OK;
+}
+
+int cmb_end_sample(cmb_ctx* c, cmb_contig_stats* stats, cmb_hist_pair* pairs, uint64_t cap, uint64_t* n_pairs) {
+  int rc = cmb_end_sample_device(c, nullptr);
+  if (rc) return rc;
+  memcpy(stats, c->rows.data(), sizeof(cmb_contig_stats) * c->rows.size());
+  if (pairs && cap >= c->pairs.size()) memcpy(pairs, c->pairs.data(), sizeof(cmb_hist_pair) * c->pairs.size());
+  if (n_pairs) *n_pairs = c->pairs.size();
+  return CMB_OK;
+}
+int cmb_fetch_pairs(cmb_ctx* c, cmb_hist_pair* pairs, uint64_t n) {
+  memcpy(pairs, c->pairs.data(), sizeof(cmb_hist_pair) * std::min<uint64_t>(n, c->pairs.size()));
+  return CMB_OK;
+}
+int cmb_get_timing(const cmb_ctx* c, cmb_sample_timing* t) {
+  *t = cmb_sample_timing{};
+  t->n_records = c->n_records;
+  t->n_intervals = c->n_intervals;
+  return CMB_OK;
+}
+void* cmb_stream(cmb_ctx*) { return nullptr; }
+
+}  // extern "C"
