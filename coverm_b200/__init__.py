@@ -1,0 +1,278 @@
+"""coverm_b200 — B200-native replacement for CoverM's per-contig coverage hot path.
+
+The product is the native library ``coverm_b200/libcoverm_b200.so`` (hand-written sm_100a CUDA kernels behind the C
+ABI declared in ``include/coverm_b200.h`` and ``include/coverm_b200_host.h``) plus the ``coverm_b200/bin/coverm``
+command-line binary.  This module is only a thin ctypes binding over that ABI for tests, ``bench.py`` and
+``__graft_entry__.py``; there is no Python or CPU fallback — importing works anywhere, but every compute entry
+point raises if the library or a CUDA device is missing.
+"""
+import ctypes as C
+import os
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(ROOT, "libcoverm_b200.so")
+COVERM_BIN = os.path.join(ROOT, "bin", "coverm")
+BAMGEN_BIN = os.path.join(ROOT, "bin", "bamgen")
+
+CMBH_MAX_SAMPLES = 64
+
+
+class CmbError(RuntimeError):
+    pass
+
+
+# ---------------------------------------------------------------------------------------------- device ABI structs
+class DeviceCfg(C.Structure):
+    _fields_ = [("device", C.c_int32), ("batch_records", C.c_uint32), ("batch_intervals", C.c_uint32),
+                ("n_staging", C.c_uint32)]
+
+
+class Params(C.Structure):
+    _fields_ = [("include_improper_pairs", C.c_uint8), ("include_supplementary", C.c_uint8),
+                ("include_secondary", C.c_uint8), ("filtering", C.c_uint8), ("min_mapq", C.c_uint8),
+                ("reserved0", C.c_uint8 * 3), ("min_aligned_length_single", C.c_uint32),
+                ("min_percent_identity_single", C.c_float), ("min_aligned_percent_single", C.c_float),
+                ("min_aligned_length_pair", C.c_uint32), ("min_percent_identity_pair", C.c_float),
+                ("min_aligned_percent_pair", C.c_float), ("contig_end_exclusion", C.c_uint64),
+                ("trim_min", C.c_float), ("trim_max", C.c_float), ("want", C.c_uint32), ("reserved1", C.c_uint32)]
+
+
+class FilterMode(C.Structure):
+    _fields_ = [("filter_single_reads", C.c_uint8), ("filter_pairs", C.c_uint8)]
+
+
+class ReadBatch(C.Structure):
+    _fields_ = [("capacity_records", C.c_uint32), ("capacity_intervals", C.c_uint32),
+                ("tid", C.c_void_p), ("pos", C.c_void_p), ("flag", C.c_void_p), ("mapq", C.c_void_p),
+                ("nm_state", C.c_void_p), ("nm", C.c_void_p), ("l_seq", C.c_void_p), ("aligned", C.c_void_p),
+                ("del_", C.c_void_p), ("ins", C.c_void_p), ("iv_begin", C.c_void_p), ("iv_start", C.c_void_p),
+                ("iv_len", C.c_void_p)]
+
+
+class ContigStats(C.Structure):
+    _fields_ = [("n_records", C.c_uint64), ("n_primary", C.c_uint64), ("n_nonsupp", C.c_uint64),
+                ("sum_edit", C.c_uint64), ("sum_indel", C.c_uint64), ("sum_identity_primary", C.c_double),
+                ("sum_identity_nonsupp", C.c_double), ("sum_depth_window", C.c_uint64),
+                ("covered_window", C.c_uint64), ("covered_full", C.c_uint64), ("trimmed_total", C.c_uint64),
+                ("trim_min_index", C.c_uint64), ("trim_max_index", C.c_uint64), ("var_k", C.c_uint64),
+                ("var_ex", C.c_uint64), ("var_ex2", C.c_uint64), ("hist_offset", C.c_uint64),
+                ("hist_count", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+class SampleTiming(C.Structure):
+    _fields_ = [("ms_zero", C.c_float), ("ms_accumulate", C.c_float), ("ms_scan", C.c_float),
+                ("ms_finalize", C.c_float), ("ms_total", C.c_float), ("arena_elems", C.c_uint64),
+                ("n_records", C.c_uint64), ("n_intervals", C.c_uint64), ("k1_launches", C.c_uint32),
+                ("k2_launches", C.c_uint32), ("k3_launches", C.c_uint32), ("reserved", C.c_uint32)]
+
+
+# ---------------------------------------------------------------------------------------------- host ABI structs
+class MemInput(C.Structure):
+    _fields_ = [("path", C.c_char_p), ("data", C.c_void_p), ("size", C.c_size_t)]
+
+
+class SampleInfo(C.Structure):
+    _fields_ = [("num_mapped_reads", C.c_uint64), ("num_reads", C.c_uint64), ("n_records", C.c_uint64),
+                ("total_s", C.c_double), ("decode_s", C.c_double), ("submit_wait_s", C.c_double),
+                ("end_sample_s", C.c_double), ("k0_ms", C.c_float), ("k1_ms", C.c_float), ("k2_ms", C.c_float),
+                ("k3_ms", C.c_float), ("device_total_ms", C.c_float), ("k1_launches", C.c_uint32),
+                ("k2_launches", C.c_uint32), ("k3_launches", C.c_uint32), ("arena_elems", C.c_uint64),
+                ("n_intervals", C.c_uint64)]
+
+
+class HostResult(C.Structure):
+    _fields_ = [("status", C.c_int32), ("out", C.c_void_p), ("out_len", C.c_size_t), ("err", C.c_void_p),
+                ("err_len", C.c_size_t), ("n_samples", C.c_uint32), ("samples", SampleInfo * CMBH_MAX_SAMPLES)]
+
+
+DEVICE_SYMBOLS = ["cmb_abi_version", "cmb_create", "cmb_destroy", "cmb_last_error", "cmb_set_reference",
+                  "cmb_set_params", "cmb_begin_sample", "cmb_acquire_batch", "cmb_submit_batch",
+                  "cmb_submit_device_batch", "cmb_end_sample", "cmb_fetch_pairs", "cmb_end_sample_device",
+                  "cmb_get_timing", "cmb_stream"]
+HOST_SYMBOLS = ["cmbh_session_create", "cmbh_session_destroy", "cmbh_last_error", "cmbh_session_set_shard",
+                "cmbh_run", "cmbh_free_result", "cmbh_main"]
+
+_lib = None
+
+
+def load_library():
+    """Load libcoverm_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if it is missing."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise CmbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                       "(there is no Python/CPU fallback)")
+    lib = C.CDLL(LIB_PATH)
+    lib.cmb_abi_version.restype = C.c_int
+    lib.cmb_create.argtypes = [C.POINTER(DeviceCfg), C.POINTER(C.c_void_p)]
+    lib.cmb_destroy.argtypes = [C.c_void_p]
+    lib.cmb_destroy.restype = None
+    lib.cmb_last_error.argtypes = [C.c_void_p]
+    lib.cmb_last_error.restype = C.c_char_p
+    lib.cmb_set_reference.argtypes = [C.c_void_p, C.c_uint32, C.POINTER(C.c_uint64), C.c_uint32, C.c_uint32]
+    lib.cmb_set_params.argtypes = [C.c_void_p, C.POINTER(Params), C.POINTER(FilterMode)]
+    lib.cmb_begin_sample.argtypes = [C.c_void_p]
+    lib.cmb_acquire_batch.argtypes = [C.c_void_p, C.POINTER(ReadBatch)]
+    lib.cmb_submit_batch.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.cmb_submit_device_batch.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.c_uint32, C.c_uint32]
+    lib.cmb_end_sample.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64, C.POINTER(C.c_uint64)]
+    lib.cmb_fetch_pairs.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+    lib.cmb_end_sample_device.argtypes = [C.c_void_p, C.POINTER(C.c_void_p)]
+    lib.cmb_get_timing.argtypes = [C.c_void_p, C.POINTER(SampleTiming)]
+    lib.cmb_stream.argtypes = [C.c_void_p]
+    lib.cmb_stream.restype = C.c_void_p
+    lib.cmbh_session_create.argtypes = [C.c_int, C.c_int, C.POINTER(C.c_void_p)]
+    lib.cmbh_session_destroy.argtypes = [C.c_void_p]
+    lib.cmbh_session_destroy.restype = None
+    lib.cmbh_last_error.restype = C.c_char_p
+    lib.cmbh_session_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
+    lib.cmbh_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(MemInput), C.c_int,
+                             C.POINTER(HostResult)]
+    lib.cmbh_free_result.argtypes = [C.POINTER(HostResult)]
+    lib.cmbh_free_result.restype = None
+    _lib = lib
+    return lib
+
+
+class RunResult:
+    def __init__(self, status, out, err, samples):
+        self.status, self.out, self.err, self.samples = status, out, err, samples
+
+
+class Session:
+    """One GPU context + host thread pool (cmbh_session): ``run(argv)`` is `coverm <argv...>` in-process."""
+
+    def __init__(self, device=0, threads=None):
+        lib = load_library()
+        self._lib = lib
+        self._h = C.c_void_p()
+        threads = threads or (os.cpu_count() or 1)
+        rc = lib.cmbh_session_create(int(device), int(threads), C.byref(self._h))
+        if rc != 0:
+            raise CmbError("cmbh_session_create failed: " + lib.cmbh_last_error().decode())
+
+    def set_shard(self, tid_begin, tid_end):
+        self._lib.cmbh_session_set_shard(self._h, tid_begin, tid_end)
+
+    def run(self, argv, memory_inputs=None):
+        """memory_inputs: {path: bytes-like (e.g. numpy uint8 array / bytes)} read instead of the filesystem."""
+        lib = self._lib
+        args = (C.c_char_p * len(argv))(*[a.encode() for a in argv])
+        mem = None
+        keep = []
+        n_mem = 0
+        if memory_inputs:
+            n_mem = len(memory_inputs)
+            mem = (MemInput * n_mem)()
+            for i, (path, buf) in enumerate(memory_inputs.items()):
+                if hasattr(buf, "ctypes"):  # numpy array
+                    ptr, size = buf.ctypes.data, buf.nbytes
+                else:
+                    cb = (C.c_char * len(buf)).from_buffer_copy(buf)
+                    keep.append(cb)
+                    ptr, size = C.addressof(cb), len(buf)
+                mem[i].path = path.encode()
+                mem[i].data = ptr
+                mem[i].size = size
+        res = HostResult()
+        rc = lib.cmbh_run(self._h, len(argv), args, mem, n_mem, C.byref(res))
+        if rc != 0:
+            raise CmbError(f"cmbh_run failed with {rc}")
+        out = C.string_at(res.out, res.out_len).decode() if res.out else ""
+        err = C.string_at(res.err, res.err_len).decode() if res.err else ""
+        samples = []
+        for i in range(res.n_samples):
+            s = res.samples[i]
+            samples.append({f[0]: getattr(s, f[0]) for f in SampleInfo._fields_})
+        status = res.status
+        lib.cmbh_free_result(C.byref(res))
+        return RunResult(status, out, err, samples)
+
+    def close(self):
+        if self._h:
+            self._lib.cmbh_session_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class DeviceContext:
+    """Direct binding of the device-level ABI (cmb_*), used by bench.py for device-resident timing."""
+
+    def __init__(self, device=0, batch_records=1 << 20, batch_intervals=0, n_staging=2):
+        lib = load_library()
+        self._lib = lib
+        self._h = C.c_void_p()
+        cfg = DeviceCfg(device, batch_records, batch_intervals, n_staging)
+        rc = lib.cmb_create(C.byref(cfg), C.byref(self._h))
+        if rc != 0:
+            raise CmbError("cmb_create failed: " + lib.cmb_last_error(None).decode())
+        self.n_contigs = 0
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise CmbError(f"{what} failed ({rc}): " + self._lib.cmb_last_error(self._h).decode())
+
+    def set_reference(self, lens, tid_begin=0, tid_end=None):
+        import numpy as np
+        lens = np.ascontiguousarray(lens, dtype=np.uint64)
+        self.n_contigs = len(lens)
+        tid_end = self.n_contigs if tid_end is None else tid_end
+        self._check(self._lib.cmb_set_reference(self._h, self.n_contigs, lens.ctypes.data_as(C.POINTER(C.c_uint64)),
+                                                tid_begin, tid_end), "cmb_set_reference")
+
+    def set_params(self, params):
+        mode = FilterMode()
+        self._check(self._lib.cmb_set_params(self._h, C.byref(params), C.byref(mode)), "cmb_set_params")
+        return mode
+
+    def begin_sample(self):
+        self._check(self._lib.cmb_begin_sample(self._h), "cmb_begin_sample")
+
+    def submit_device_batch(self, batch, n_records, n_intervals):
+        self._check(self._lib.cmb_submit_device_batch(self._h, C.byref(batch), n_records, n_intervals),
+                    "cmb_submit_device_batch")
+
+    def acquire_batch(self):
+        b = ReadBatch()
+        self._check(self._lib.cmb_acquire_batch(self._h, C.byref(b)), "cmb_acquire_batch")
+        return b
+
+    def submit_batch(self, n_records, n_intervals):
+        self._check(self._lib.cmb_submit_batch(self._h, n_records, n_intervals), "cmb_submit_batch")
+
+    def end_sample_device(self):
+        p = C.c_void_p()
+        self._check(self._lib.cmb_end_sample_device(self._h, C.byref(p)), "cmb_end_sample_device")
+        return p.value
+
+    def end_sample(self):
+        import numpy as np
+        rows = np.zeros(self.n_contigs, dtype=np.dtype(ContigStats))
+        n_pairs = C.c_uint64()
+        self._check(self._lib.cmb_end_sample(self._h, rows.ctypes.data, None, 0, C.byref(n_pairs)), "cmb_end_sample")
+        return rows, n_pairs.value
+
+    def timing(self):
+        t = SampleTiming()
+        self._lib.cmb_get_timing(self._h, C.byref(t))
+        return {f[0]: getattr(t, f[0]) for f in SampleTiming._fields_}
+
+    def stream(self):
+        return self._lib.cmb_stream(self._h)
+
+    def close(self):
+        if self._h:
+            self._lib.cmb_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

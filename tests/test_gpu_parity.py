@@ -1,0 +1,143 @@
+"""Parity of the CUDA path (libcoverm_b200.so through its C ABI / the `coverm` binary) with
+ (1) the reference's own golden vectors (tests/golden/reference_cases.py), and
+ (2) the CPU oracle on seeded synthetic BAMs (bamgen) that exercise what the tiny fixtures cannot: contigs spanning
+     many 8192-element chunks, chunks holding many contigs, deep pile-ups, every filter mode, genome modes.
+Outputs are compared as text: identical digit strings mean bit-exact integers AND bit-identical f32 results
+(stronger than the 1e-6 relative tolerance BASELINE.json asks for floating-point methods)."""
+import os
+import subprocess
+
+import pytest
+
+import coverm_b200
+from case_runner import DATA, ORACLE_BIN, check_case, run_case
+from reference_cases import CASES, CLI_CASES
+
+pytestmark = pytest.mark.gpu
+
+GPU_CASES = [c for c in CASES + CLI_CASES if c["sub"] in ("contig", "genome")]
+
+
+@pytest.mark.parametrize("case", GPU_CASES, ids=[f"{c['sub']}@{c['ref']}" for c in GPU_CASES])
+def test_cuda_path_matches_reference_golden(case):
+    check_case(case, run_case(coverm_b200.COVERM_BIN, case, extra_args=["-t", "4"]))
+
+
+# ---------------------------------------------------------------------------------------------- GPU vs oracle
+def _both(argv, threads="8"):
+    g = subprocess.run([coverm_b200.COVERM_BIN] + argv + ["-t", threads, "--print-reads-mapped"], capture_output=True,
+                       text=True, timeout=900)
+    o = subprocess.run([ORACLE_BIN] + argv + ["-t", threads, "--print-reads-mapped"], capture_output=True, text=True,
+                       timeout=900)
+    return g, o
+
+
+def _assert_same(argv):
+    g, o = _both(argv)
+    assert g.returncode == o.returncode, f"{argv}: exit {g.returncode} vs oracle {o.returncode}\n{g.stderr[-1500:]}"
+    if g.stdout != o.stdout:
+        gl, ol = g.stdout.splitlines(), o.stdout.splitlines()
+        diff = [(i, a, b) for i, (a, b) in enumerate(zip(gl, ol)) if a != b][:8]
+        raise AssertionError(f"{argv}: {len(gl)} vs {len(ol)} lines; first differences (line, gpu, oracle): {diff}")
+    rm = lambda p: [l for l in p.stderr.splitlines() if l.startswith("#reads_mapped")]
+    assert rm(g) == rm(o)
+
+
+ALL_METHODS = ["mean", "trimmed_mean", "covered_fraction", "covered_bases", "variance", "length", "count",
+               "reads_per_base", "rpkm", "tpm", "anir"]
+
+FIXTURE_RUNS = [
+    ["contig", "-m"] + ALL_METHODS + ["-b", DATA + "/1.bam"],
+    ["contig", "-m"] + ALL_METHODS + ["-b", DATA + "/eg2.bam", "--output-format", "sparse"],
+    ["contig", "-m", "mean", "variance", "-b", DATA + "/1.bam", "--min-read-percent-identity", "95",
+     "--min-read-aligned-length", "50"],
+    ["contig", "-m", "mean", "trimmed_mean", "-b", DATA + "/eg2.bam", "--proper-pairs-only",
+     "--min-read-percent-identity-pair", "0.9", "--min-read-aligned-length-pair", "100"],
+    ["contig", "-m", "coverage_histogram", "-b", DATA + "/1read_of_pair_mapped.bam"],
+    ["contig", "-m", "metabat", "-b", DATA + "/1.bam", DATA + "/1read_of_pair_mapped.bam"][:5],
+    ["genome", "--single-genome", "-m", "mean", "trimmed_mean", "variance", "covered_fraction", "-b", DATA + "/1.bam",
+     "--min-covered-fraction", "0"],
+    ["contig", "-m", "mean", "trimmed_mean", "--contig-end-exclusion", "0", "--trim-min", "10", "--trim-max", "90",
+     "-b", DATA + "/1.bam", "--no-zeros"],
+]
+
+
+@pytest.mark.parametrize("argv", FIXTURE_RUNS, ids=[" ".join(a[:6]).replace(DATA + "/", "") + f"#{i}" for i, a in enumerate(FIXTURE_RUNS)])
+def test_cuda_path_matches_oracle_on_reference_fixtures(argv):
+    _assert_same(argv)
+
+
+@pytest.fixture(scope="module")
+def synth(tmp_path_factory):
+    d = tmp_path_factory.mktemp("synth")
+    out = {}
+
+    def gen(name, *args):
+        p = str(d / f"{name}.bam")
+        subprocess.check_call([coverm_b200.BAMGEN_BIN, "--out", p, "--threads", "8"] + [str(a) for a in args],
+                              stdout=subprocess.DEVNULL)
+        out[name] = p
+
+    # many small contigs (several per chunk), a few long ones (hundreds of chunks), deep coverage, genomes
+    gen("small", "--contigs", 3000, "--reads", 200000, "--seed", 11, "--median-len", 2500, "--min-len", 200, "--max-len", 60000)
+    gen("tiny", "--contigs", 4000, "--reads", 60000, "--seed", 12, "--median-len", 300, "--min-len", 90, "--max-len", 2000, "--read-len", 80)
+    gen("long", "--contigs", 12, "--reads", 300000, "--seed", 13, "--median-len", 900000, "--sigma", 0.6, "--min-len", 50000, "--max-len", 5000000)
+    gen("deep", "--contigs", 40, "--reads", 600000, "--seed", 14, "--median-len", 9000, "--min-len", 2000, "--max-len", 40000)
+    gen("mags", "--contigs", 2500, "--genomes", 60, "--reads", 250000, "--seed", 15, "--median-len", 8000, "--definition-out", str(d / "mags.tsv"))
+    out["mags_def"] = str(d / "mags.tsv")
+    return out
+
+
+SYNTH_RUNS = [
+    ("small", ["contig", "-m"] + ALL_METHODS),
+    ("small", ["contig", "-m", "mean", "trimmed_mean", "variance", "--contig-end-exclusion", "0"]),
+    ("small", ["contig", "-m", "mean", "trimmed_mean", "covered_fraction", "--min-read-percent-identity", "97", "--min-mapq", "20"]),
+    ("small", ["contig", "-m", "mean", "variance", "--proper-pairs-only", "--min-read-aligned-length-pair", "250", "--min-read-percent-identity-pair", "95"]),
+    ("small", ["contig", "-m", "mean", "count", "--proper-pairs-only", "--min-mapq", "30", "--min-read-aligned-percent", "95"]),
+    ("small", ["contig", "-m", "mean", "trimmed_mean", "--exclude-supplementary", "--include-secondary", "--no-zeros", "--output-format", "sparse"]),
+    ("small", ["contig", "-m", "coverage_histogram"]),
+    ("small", ["contig", "-m", "metabat"]),
+    ("tiny", ["contig", "-m"] + ALL_METHODS),
+    ("tiny", ["contig", "-m", "mean", "trimmed_mean", "variance", "--contig-end-exclusion", "10", "--trim-min", "0.2", "--trim-max", "0.8"]),
+    ("long", ["contig", "-m"] + ALL_METHODS),
+    ("long", ["contig", "-m", "coverage_histogram"]),
+    ("deep", ["contig", "-m", "mean", "trimmed_mean", "variance", "covered_fraction"]),
+    ("deep", ["contig", "-m", "coverage_histogram", "--min-covered-fraction", "0"]),
+    ("mags", ["genome", "-s", "~", "-m", "relative_abundance", "mean", "trimmed_mean", "variance", "covered_fraction", "covered_bases", "length", "count", "rpkm", "tpm", "--min-covered-fraction", "0"]),
+    ("mags", ["genome", "-s", "~", "-m", "mean", "trimmed_mean", "--min-read-percent-identity", "95", "--output-format", "sparse", "--no-zeros"]),
+    ("mags", ["genome", "--genome-definition", "{mags_def}", "-m", "relative_abundance", "mean", "trimmed_mean", "variance", "--min-covered-fraction", "5"]),
+    ("mags", ["genome", "-s", "~", "-m", "coverage_histogram"]),
+    ("mags", ["genome", "--single-genome", "-m", "mean", "variance", "trimmed_mean", "--min-covered-fraction", "0"]),
+]
+
+
+@pytest.mark.parametrize("which,argv", SYNTH_RUNS, ids=[f"{w}:{' '.join(a[:7])}#{i}" for i, (w, a) in enumerate(SYNTH_RUNS)])
+def test_cuda_path_matches_oracle_on_synthetic_bams(synth, which, argv):
+    argv = [a.replace("{mags_def}", synth["mags_def"]) for a in argv]
+    _assert_same(argv + ["-b", synth[which]])
+
+
+def test_multiple_samples_reuse_the_arena(synth):
+    # second sample runs on the arena that K2 re-zeroed while scanning the first (clean-as-you-go)
+    _assert_same(["contig", "-m", "mean", "trimmed_mean", "variance", "--output-format", "sparse", "-b", synth["small"],
+                  synth["deep"], synth["small"]])
+    _assert_same(["contig", "-m", "mean", "trimmed_mean", "-b", DATA + "/7seqs.reads_for_seq1.bam",
+                  DATA + "/7seqs.reads_for_seq1_and_seq2.bam"])
+
+
+def test_in_memory_bam_through_the_c_abi(synth):
+    import numpy as np
+    buf = np.fromfile(synth["small"], dtype=np.uint8)
+    argv = ["contig", "-m", "mean", "trimmed_mean", "covered_fraction", "-b", synth["small"]]
+    sess = coverm_b200.Session(device=0, threads=8)
+    r1 = sess.run(argv, memory_inputs={synth["small"]: buf})
+    r2 = sess.run(argv)
+    sess.close()
+    want = subprocess.run([ORACLE_BIN] + argv, capture_output=True, text=True, check=True).stdout
+    assert r1.status == 0 and r1.out == want and r2.out == want
+    assert r1.samples[0]["k2_launches"] == 1 and r1.samples[0]["k1_launches"] >= 1
+
+
+def test_smoke_entry():
+    import __graft_entry__
+    __graft_entry__.smoke()
