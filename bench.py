@@ -1,0 +1,357 @@
+#!/usr/bin/env python
+"""bench.py — reads/sec of `coverm contig -m mean trimmed_mean covered_fraction` (BASELINE.json configs[1]).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+One "step" = one pass of the coverage hot path over one synthetic sample (500 000 contigs / ~10 M records).
+  value   whole-job reads/s with the per-read tuples already resident in HBM (device arm: K0 zero-fill of the row
+          table, K1 filter+delta, K1b chunk carries, K2 TMA-staged segmented scan + reductions, K3 per-contig finalise;
+          for N > 1 also the NCCL all-gather of the per-contig table), timed with CUDA events on the library's stream.
+  e2e     the same metric through the public C ABI call a user makes (cmbh_run == `coverm contig ... -b sample.bam`):
+          BAM bytes in a HOST buffer -> BGZF inflate + BAM decode on the host cores -> pinned SoA tuples -> H2D ->
+          kernels -> D2H of the table -> printed TSV in a host buffer.  Wall clock, everything inside.
+  roofline / cpu_baseline as described in DESIGN.md §Measurement.
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads for BGZF inflate, the record
+loop single-threaded exactly as the reference's) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "reads/sec `coverm contig` (mean+trimmed_mean+covered_fraction)"
+METHODS = ["mean", "trimmed_mean", "covered_fraction"]
+CONTIG_END_EXCLUSION = 75
+TRIM = (0.05, 0.95)
+
+
+def log(*a):
+    print("[bench]", *a, file=sys.stderr, flush=True)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi SM clock / throttle-reason sampling during the timed regions."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.stop_flag, self.max_mhz = index, [], set(), False, None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag:
+            try:
+                o = subprocess.run(["nvidia-smi", f"--query-gpu={q}", "--format=csv,noheader,nounits", "-i", str(self.index)],
+                                   capture_output=True, text=True, timeout=5).stdout.strip().split(",")
+                self.samples.append(float(o[0]))
+                self.max_mhz = float(o[1])
+                for n, v in zip(names, o[2:]):
+                    if v.strip().lower().startswith("active"):
+                        self.reasons.add(n)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        s = sorted(self.samples)
+        return {"sm_mhz": s[len(s) // 2] if s else None, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def gen_bam(path, contigs, reads, seed, threads):
+    import coverm_b200
+    t = time.time()
+    meta = path + ".json"
+    if os.path.exists(path) and os.path.exists(meta):  # same (contigs, reads, seed) already generated in this workdir
+        info = json.load(open(meta))
+        if info.get("key") == [contigs, reads, seed]:
+            info["gen_s"] = 0.0
+            return info
+    out = subprocess.run([coverm_b200.BAMGEN_BIN, "--out", path, "--contigs", str(contigs), "--reads", str(reads), "--seed",
+                          str(seed), "--median-len", "4000", "--sigma", "0.8", "--min-len", "1000", "--max-len", "2000000",
+                          "--threads", str(threads)], capture_output=True, text=True, check=True).stdout
+    info = json.loads(out)
+    info["gen_s"] = round(time.time() - t, 2)
+    info["bam_bytes"] = os.path.getsize(path)
+    info["key"] = [contigs, reads, seed]
+    json.dump(info, open(meta, "w"))
+    return info
+
+
+def coverm_argv(bam, threads):
+    return ["contig", "-m"] + METHODS + ["-b", bam, "-t", str(threads)]
+
+
+def run_reference_arm(args, workdir, threads):
+    """The reference's CPU path (oracle restatement) on a bounded sample: 1/10 of the contigs and reads."""
+    contigs, reads = max(1, args.contigs // args.cpu_fraction), max(1, args.reads // args.cpu_fraction)
+    bam = os.path.join(workdir, f"cpu_sample_{contigs}_{reads}.bam")
+    info = gen_bam(bam, contigs, reads, args.seed + 100, threads)
+    oracle = os.path.join(ROOT, "oracle", "coverm_oracle")
+    argv = [oracle] + coverm_argv(bam, threads)
+    outs = []
+    times = []
+    for i in range(args.warmup_cpu + args.steps_cpu):
+        t = time.perf_counter()
+        p = subprocess.run(argv, capture_output=True, text=True, check=True)
+        dt = time.perf_counter() - t
+        if i >= args.warmup_cpu:
+            times.append(dt)
+        outs.append(p.stdout)
+    sec = sum(times) / len(times)
+    return {"value": info["records"] / sec, "unit": "reads/s", "cores": threads, "kind": "port",
+            "sample": f"{contigs} contigs / {info['bases']} bp / {info['records']} records (1/{args.cpu_fraction} of the workload, "
+                      f"same generator), oracle/coverm_oracle -t {threads}: {threads} BGZF inflate threads, single-threaded record loop "
+                      f"+ one O(L) pass per estimator as in the reference; mean of {len(times)} runs",
+            "seconds_per_run": sec}, bam, outs[-1]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--contigs", type=int, default=500000)
+    ap.add_argument("--reads", type=int, default=10000000)
+    ap.add_argument("--seed", type=int, default=20260925)
+    ap.add_argument("--cpu-fraction", type=int, default=10)
+    ap.add_argument("--steps-cpu", type=int, default=2)
+    ap.add_argument("--warmup-cpu", type=int, default=0)
+    ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
+    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--workdir", default=os.environ.get("CMB_BENCH_DIR", "/tmp/coverm_b200_bench"))
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    ncpu = os.cpu_count() or 1
+    threads = max(1, ncpu // world)
+    os.makedirs(args.workdir, exist_ok=True)
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        cpu, _, _ = run_reference_arm(args, args.workdir, ncpu)
+        line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "reads/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["seconds_per_run"] * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+                "config": {"workload": f"coverm contig -m {' '.join(METHODS)} on a synthetic sorted BAM; bounded sample: {cpu['sample']}",
+                           "contigs": args.contigs // args.cpu_fraction, "reads": args.reads // args.cpu_fraction},
+                "cpu_baseline": cpu,
+                "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line), flush=True)
+        return
+
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    import coverm_b200
+    from coverm_b200 import ContigStats, Params, ReadBatch
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
+    torch.cuda.set_device(local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
+
+    # ---------------------------------------------------------------- workload: one sample per GPU (weak scaling)
+    bam = os.path.join(args.workdir, f"sample_r{rank}_{args.contigs}_{args.reads}.bam")
+    info = gen_bam(bam, args.contigs, args.reads, args.seed + rank, threads)
+    log(f"rank {rank}: generated {bam}: {info}")
+    bam_bytes = np.fromfile(bam, dtype=np.uint8)  # HOST buffer handed to the C ABI
+    t0 = time.time()
+    tup = coverm_b200.extract_tuples(bam, threads)
+    n_rec, n_iv = int(tup["n_records"]), int(tup["n_intervals"])
+    lens = tup["contig_len"]
+    log(f"rank {rank}: {n_rec} records, {n_iv} intervals, {len(lens)} contigs, {int(lens.sum())} bp; tuple extraction {time.time() - t0:.2f}s")
+
+    # ---------------------------------------------------------------- device arm: tuples resident in HBM
+    dev = {k: torch.from_numpy(tup[k]).cuda() for k in ["tid", "pos", "flag", "mapq", "nm_state", "nm", "l_seq", "aligned",
+                                                         "del_", "ins", "iv_begin", "iv_start", "iv_len"]}
+    batch = ReadBatch()
+    batch.capacity_records, batch.capacity_intervals = n_rec, n_iv
+    for k, tns in dev.items():
+        setattr(batch, k, tns.data_ptr())
+    ctx = coverm_b200.DeviceContext(device=local_rank, batch_records=1 << 16, n_staging=2)
+    ctx.set_reference(lens)
+    prm = Params()
+    prm.include_improper_pairs, prm.include_supplementary, prm.include_secondary = 1, 1, 0
+    prm.filtering, prm.min_mapq = 0, 255
+    prm.contig_end_exclusion = CONTIG_END_EXCLUSION
+    prm.trim_min, prm.trim_max = TRIM
+    prm.want = 1  # CMB_WANT_HIST (trimmed_mean)
+    ctx.set_params(prm)
+    stream = torch.cuda.ExternalStream(ctx.stream())
+    row_bytes = len(lens) * C_sizeof(ContigStats)
+    gathered = torch.empty(world * row_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+
+    def device_step():
+        ctx.begin_sample()
+        ctx.submit_device_batch(batch, n_rec, n_iv)
+        ptr = ctx.end_sample_device()  # K1c/K1b/K2/K3 + error check (stream-synchronous)
+        if world > 1:  # the single collective of the path: all-gather of the per-contig table over NVLink
+            dist.all_gather_into_tensor(gathered, _device_view(ptr, row_bytes, local_rank))
+        return ptr
+
+    sampler = ClockSampler(local_rank)
+    for _ in range(max(3, args.warmup)):
+        device_step()
+    torch.cuda.synchronize()
+    barrier()
+    sampler.start()
+    k2_ms, k1_ms, k3_ms, k0_ms, dev_ms = [], [], [], [], []
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    t_wall = time.perf_counter()
+    with torch.cuda.stream(stream):
+        ev0.record()
+    launches = 0
+    for _ in range(args.steps):
+        device_step()
+        tm = ctx.timing()
+        k0_ms.append(tm["ms_zero"]); k1_ms.append(tm["ms_accumulate"]); k2_ms.append(tm["ms_scan"]); k3_ms.append(tm["ms_finalize"])
+        dev_ms.append(tm["ms_total"])
+        launches += tm["k1_launches"] + 2 + tm["k2_launches"] + tm["k3_launches"]
+    with torch.cuda.stream(stream):
+        ev1.record()
+    torch.cuda.synchronize()
+    wall_ms = (time.perf_counter() - t_wall) * 1e3
+    barrier()
+    event_ms = ev0.elapsed_time(ev1)
+    # the all-gather (N > 1) runs on torch's stream after the ctx stream has been synchronised: use the wall clock then
+    step_ms = max_over_ranks((wall_ms if world > 1 else event_ms) / args.steps)
+    total_reads = sum_over_ranks(float(n_rec))
+    value = total_reads / (step_ms * 1e-3)
+    arena_elems = ctx.timing()["arena_elems"]
+    mean = lambda v: sum(v) / len(v)
+    peak, peak_src = measured_peaks()
+    k2_mean = mean(k2_ms)
+    algo_bytes = 4.0 * arena_elems
+    achieved = algo_bytes / (k2_mean * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "k2_traffic.json")
+    if os.path.exists(tpath):
+        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+
+    # ---------------------------------------------------------------- e2e arm: BAM bytes in host memory -> TSV
+    sess = coverm_b200.Session(device=local_rank, threads=threads)
+    argv = coverm_argv(bam, threads)
+    e2e_steps = args.e2e_steps or args.steps
+    res = None
+    for _ in range(max(1, min(2, args.warmup))):
+        res = sess.run(argv, memory_inputs={bam: bam_bytes})
+    if res.status != 0:
+        raise SystemExit(f"coverm_b200 failed: {res.err}")
+    torch.cuda.synchronize()
+    barrier()
+    t_e = time.perf_counter()
+    breakdown = []
+    for _ in range(e2e_steps):
+        res = sess.run(argv, memory_inputs={bam: bam_bytes})
+        breakdown.append(res.samples[0])
+    torch.cuda.synchronize()
+    e2e_s = (time.perf_counter() - t_e) / e2e_steps
+    barrier()
+    e2e_s = max_over_ranks(e2e_s)
+    sampler.stop_flag = True
+    sampler.join(timeout=2)
+    s0 = breakdown[-1]
+    e2e_value = total_reads / e2e_s
+    h2d = 39 * s0["n_records"] + 4 + 8 * s0["n_intervals"]
+    d2h = row_bytes
+
+    # ---------------------------------------------------------------- CPU baseline + parity check on the bounded sample
+    cpu = None
+    parity = None
+    if rank == 0 and world == 1 and not args.skip_cpu_baseline:
+        cpu, cpu_bam, oracle_out = run_reference_arm(args, args.workdir, ncpu)
+        mine = sess.run(coverm_argv(cpu_bam, threads))
+        parity = (mine.status == 0 and mine.out == oracle_out)
+        if not parity:
+            log("PARITY FAILURE on the bounded sample: GPU output differs from the oracle")
+    sess.close()
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
+            "data": "synthetic",
+            "config": {"workload": f"configs[1]: coverm contig -m {' '.join(METHODS)} on a synthetic reference-sorted BAM, "
+                                   f"{args.contigs} contigs / {info['bases']} bp / {n_rec} records per GPU (one sample per GPU)",
+                       "contigs": args.contigs, "reads_per_gpu": n_rec, "bases_per_gpu": int(info["bases"]),
+                       "parallelism": f"{world} sample(s), one per GPU" + ("; NCCL all-gather of the per-contig table" if world > 1 else ""),
+                       "l2": f"inputs larger than L2: {algo_bytes / 1e9:.1f} GB delta arena + {(39 * n_rec + 8 * n_iv) / 1e6:.0f} MB tuples per step",
+                       "host_threads_per_rank": threads},
+            "clocks": sampler.summary(),
+            "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+                    "seconds_per_step": e2e_s,
+                    "breakdown_last_step": {k: s0[k] for k in ["total_s", "decode_s", "submit_wait_s", "end_sample_s", "k0_ms", "k1_ms",
+                                                               "k2_ms", "k3_ms", "device_total_ms"]},
+                    "input": f"BAM bytes ({len(bam_bytes)} B) in host memory, cmbh_run (== `coverm contig`), TSV text out"},
+            "gpu_launches": int(launches),
+            "roofline": {"bound": "hbm", "kernel": "k2_scan_reduce<HIST,CLEAN>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": k2_mean},
+            "device_breakdown_ms": {"k0_zero": mean(k0_ms), "k1_filter_delta+carry": mean(k1_ms), "k2_scan_reduce": k2_mean,
+                                    "k3_finalize": mean(k3_ms), "stream_total": mean(dev_ms), "wall_per_step": wall_ms / args.steps},
+            "cpu_baseline": cpu, "parity_vs_oracle_on_cpu_sample": parity,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def C_sizeof(t):
+    import ctypes
+    return ctypes.sizeof(t)
+
+
+def _device_view(ptr, nbytes, device_index):
+    """A torch uint8 tensor aliasing `nbytes` of device memory at `ptr` (the library's per-contig row table)."""
+    import torch
+
+    class _Holder:
+        pass
+
+    h = _Holder()
+    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
+    return torch.as_tensor(h, device=torch.device("cuda", device_index))
+
+
+if __name__ == "__main__":
+    main()

@@ -89,8 +89,34 @@ DEVICE_SYMBOLS = ["cmb_abi_version", "cmb_create", "cmb_destroy", "cmb_last_erro
                   "cmb_set_params", "cmb_begin_sample", "cmb_acquire_batch", "cmb_submit_batch",
                   "cmb_submit_device_batch", "cmb_end_sample", "cmb_fetch_pairs", "cmb_end_sample_device",
                   "cmb_get_timing", "cmb_stream"]
+class Tuples(C.Structure):
+    _fields_ = [("n_contigs", C.c_uint32), ("contig_len", C.POINTER(C.c_uint64)), ("n_records", C.c_uint64),
+                ("n_intervals", C.c_uint64), ("tid", C.POINTER(C.c_int32)), ("pos", C.POINTER(C.c_int32)),
+                ("flag", C.POINTER(C.c_uint16)), ("mapq", C.POINTER(C.c_uint8)), ("nm_state", C.POINTER(C.c_uint8)),
+                ("nm", C.POINTER(C.c_uint32)), ("l_seq", C.POINTER(C.c_uint32)), ("aligned", C.POINTER(C.c_uint32)),
+                ("del_", C.POINTER(C.c_uint32)), ("ins", C.POINTER(C.c_uint32)), ("iv_begin", C.POINTER(C.c_uint32)),
+                ("iv_start", C.POINTER(C.c_int32)), ("iv_len", C.POINTER(C.c_int32))]
+
+
 HOST_SYMBOLS = ["cmbh_session_create", "cmbh_session_destroy", "cmbh_last_error", "cmbh_session_set_shard",
-                "cmbh_run", "cmbh_free_result", "cmbh_main"]
+                "cmbh_run", "cmbh_free_result", "cmbh_main", "cmbh_extract_tuples", "cmbh_free_tuples"]
+
+
+def extract_tuples(path, threads=None):
+    """Decode a BAM/SAM file into the SoA tuple columns of cmb_read_batch (host numpy arrays, no GPU)."""
+    import numpy as np
+    lib = load_library()
+    t = Tuples()
+    rc = lib.cmbh_extract_tuples(path.encode(), None, 0, int(threads or os.cpu_count() or 1), C.byref(t))
+    if rc != 0:
+        raise CmbError("cmbh_extract_tuples failed: " + lib.cmbh_last_error().decode())
+    n, ni = t.n_records, t.n_intervals
+    out = {"contig_len": np.ctypeslib.as_array(t.contig_len, (t.n_contigs,)).copy(), "n_records": n, "n_intervals": ni}
+    for name, cnt in [("tid", n), ("pos", n), ("flag", n), ("mapq", n), ("nm_state", n), ("nm", n), ("l_seq", n),
+                      ("aligned", n), ("del_", n), ("ins", n), ("iv_begin", n + 1), ("iv_start", ni), ("iv_len", ni)]:
+        out[name] = np.ctypeslib.as_array(getattr(t, name), (cnt,)).copy() if cnt else np.zeros(0, dtype=np.int32)
+    lib.cmbh_free_tuples(C.byref(t))
+    return out
 
 _lib = None
 
@@ -131,6 +157,9 @@ def load_library():
                              C.POINTER(HostResult)]
     lib.cmbh_free_result.argtypes = [C.POINTER(HostResult)]
     lib.cmbh_free_result.restype = None
+    lib.cmbh_extract_tuples.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Tuples)]
+    lib.cmbh_free_tuples.argtypes = [C.POINTER(Tuples)]
+    lib.cmbh_free_tuples.restype = None
     _lib = lib
     return lib
 

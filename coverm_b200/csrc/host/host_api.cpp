@@ -111,3 +111,103 @@ int cmbh_main(int argc, char** argv) {
 }
 
 }  // extern "C"
+
+// ---------------------------------------------------------------------------------------------------------------
+// Whole-file tuple extraction (no GPU involved): the SoA columns the device ABI consumes, for callers that want to
+// stage tuples in HBM themselves (bench.py's device-resident timing, cmb_submit_device_batch).
+extern "C" {
+
+int cmbh_extract_tuples(const char* path, const uint8_t* data, size_t size, int threads, cmbh_tuples* out) {
+  if (!path || !out) return -2;
+  memset(out, 0, sizeof *out);
+  try {
+    InputSpec in;
+    in.path = path;
+    in.data = data;
+    in.size = size;
+    ThreadPool pool(threads);
+    ByteSource bytes(in);
+    std::vector<uint8_t> sam_as_bam;
+    const uint8_t* p = bytes.data();
+    size_t n = bytes.size();
+    Header header;
+    if (!(n >= 2 && p[0] == 0x1f && p[1] == 0x8b) && SamToBam::looks_like_sam(p, n)) {
+      SamToBam::convert(p, n, header, sam_as_bam);
+      p = sam_as_bam.data();
+      n = sam_as_bam.size();
+    }
+    InflateStream stream(p, n, pool, 256u << 20);
+    std::vector<uint8_t> buf;
+    while (stream.fill(buf)) {
+    }
+    if (buf.size() < 12 || memcmp(buf.data(), "BAM\1", 4) != 0) throw Panic("not a BAM/SAM file");
+    size_t o = 12 + (size_t)rd_u32(buf.data() + 4);
+    const uint32_t n_ref = rd_u32(buf.data() + o - 4);
+    std::vector<uint64_t> lens;
+    for (uint32_t i = 0; i < n_ref; ++i) {
+      const uint32_t l_name = rd_u32(buf.data() + o);
+      lens.push_back(rd_u32(buf.data() + o + 4 + l_name));
+      o += 8 + l_name;
+    }
+    std::vector<size_t> rec_off;
+    while (o + 4 <= buf.size()) {
+      const uint32_t bs = rd_u32(buf.data() + o);
+      if (o + 4 + (size_t)bs > buf.size()) break;
+      rec_off.push_back(o);
+      o += 4 + (size_t)bs;
+    }
+    const size_t nrec = rec_off.size();
+    constexpr size_t ITEM = 8192;
+    const size_t n_items = (nrec + ITEM - 1) / ITEM;
+    struct Item { std::vector<int32_t> s, l; };
+    std::vector<Item> items(n_items);
+    auto alloc = [](size_t bytes) { return malloc(bytes ? bytes : 1); };
+    out->n_contigs = n_ref;
+    out->contig_len = (uint64_t*)alloc(8 * (size_t)n_ref);
+    memcpy(out->contig_len, lens.data(), 8 * (size_t)n_ref);
+    out->n_records = nrec;
+    out->tid = (int32_t*)alloc(4 * nrec); out->pos = (int32_t*)alloc(4 * nrec); out->flag = (uint16_t*)alloc(2 * nrec);
+    out->mapq = (uint8_t*)alloc(nrec); out->nm_state = (uint8_t*)alloc(nrec); out->nm = (uint32_t*)alloc(4 * nrec);
+    out->l_seq = (uint32_t*)alloc(4 * nrec); out->aligned = (uint32_t*)alloc(4 * nrec); out->del = (uint32_t*)alloc(4 * nrec);
+    out->ins = (uint32_t*)alloc(4 * nrec); out->iv_begin = (uint32_t*)alloc(4 * (nrec + 1));
+    pool.parallel_for(n_items, [&](size_t it, int) {
+      Tuple t;
+      for (size_t r = it * ITEM; r < std::min(nrec, (it + 1) * ITEM); ++r) {
+        const uint32_t before = (uint32_t)items[it].s.size();
+        decode_bam_record(buf.data() + rec_off[r], t, items[it].s, items[it].l);
+        out->tid[r] = t.tid; out->pos[r] = t.pos; out->flag[r] = t.flag; out->mapq[r] = t.mapq; out->nm_state[r] = t.nm_state;
+        out->nm[r] = t.nm; out->l_seq[r] = t.l_seq; out->aligned[r] = t.aligned; out->del[r] = t.del; out->ins[r] = t.ins;
+        out->iv_begin[r] = before;
+      }
+    });
+    std::vector<uint64_t> base(n_items + 1, 0);
+    for (size_t it = 0; it < n_items; ++it) base[it + 1] = base[it] + items[it].s.size();
+    const uint64_t n_iv = base[n_items];
+    if (n_iv > 0xffffffffull) throw Panic("too many intervals for 32-bit offsets");
+    out->n_intervals = n_iv;
+    out->iv_start = (int32_t*)alloc(4 * n_iv);
+    out->iv_len = (int32_t*)alloc(4 * n_iv);
+    pool.parallel_for(n_items, [&](size_t it, int) {
+      for (size_t r = it * ITEM; r < std::min(nrec, (it + 1) * ITEM); ++r) out->iv_begin[r] += (uint32_t)base[it];
+      if (!items[it].s.empty()) {
+        memcpy(out->iv_start + base[it], items[it].s.data(), 4 * items[it].s.size());
+        memcpy(out->iv_len + base[it], items[it].l.data(), 4 * items[it].l.size());
+      }
+    });
+    out->iv_begin[nrec] = (uint32_t)n_iv;
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    cmbh_free_tuples(out);
+    return -1;
+  }
+}
+
+void cmbh_free_tuples(cmbh_tuples* t) {
+  if (!t) return;
+  free(t->contig_len); free(t->tid); free(t->pos); free(t->flag); free(t->mapq); free(t->nm_state); free(t->nm);
+  free(t->l_seq); free(t->aligned); free(t->del); free(t->ins); free(t->iv_begin); free(t->iv_start); free(t->iv_len);
+  memset(t, 0, sizeof *t);
+}
+
+}  // extern "C"

@@ -60,6 +60,31 @@ int cmbh_session_set_shard(cmbh_session* s, uint32_t tid_begin, uint32_t tid_end
 int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_input* mem, int n_mem, cmbh_result* res);
 void cmbh_free_result(cmbh_result* res);
 
+/* Whole-file tuple extraction on the host (no GPU): the SoA columns of cmb_read_batch for every record of a BAM/SAM
+ * file (or memory buffer when data != NULL), for callers that stage tuples in HBM themselves and feed
+ * cmb_submit_device_batch.  All arrays are malloc'd; release with cmbh_free_tuples. */
+typedef struct cmbh_tuples {
+  uint32_t n_contigs;
+  uint64_t* contig_len;
+  uint64_t n_records;
+  uint64_t n_intervals;
+  int32_t* tid;
+  int32_t* pos;
+  uint16_t* flag;
+  uint8_t* mapq;
+  uint8_t* nm_state;
+  uint32_t* nm;
+  uint32_t* l_seq;
+  uint32_t* aligned;
+  uint32_t* del;
+  uint32_t* ins;
+  uint32_t* iv_begin; /* n_records + 1 */
+  int32_t* iv_start;
+  int32_t* iv_len;
+} cmbh_tuples;
+int cmbh_extract_tuples(const char* path, const uint8_t* data, size_t size, int threads, cmbh_tuples* out);
+void cmbh_free_tuples(cmbh_tuples* t);
+
 /* The command-line entry point (what the `coverm` binary calls). */
 int cmbh_main(int argc, char** argv);
 
