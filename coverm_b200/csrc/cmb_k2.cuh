@@ -1,0 +1,336 @@
+// K2: segmented prefix sum of the delta arena + every O(L) reduction of EST::add_contig, one pass, HBM-bound.
+//
+// Persistent CTAs (2 per SM, 512 threads).  Each CTA claims 8192-element chunks with an atomic ticket and keeps a
+// 3-stage ring of 32 KB tiles in flight with TMA (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx).  A
+// thread owns one 16-element span (4 x LDS.128, conflict-free through the swizzle); contigs start on span boundaries,
+// so a span never straddles two contigs.  Running depth at a span = chunk carry (K1b) + segmented warp/CTA scan of the
+// span totals.  Depth is piecewise constant, so everything is accumulated per RUN (a run ends where a delta is
+// non-zero, ~1-2 % of positions): covered bases, sum of depth, and the depth histogram of the end-trimmed window, which
+// lives in shared memory per (contig slot, depth bin) and is flushed as (depth,count) records while the next chunk is
+// being scanned (double-buffered, so the chunk loop has a single __syncthreads).
+#pragma once
+
+struct K2Args {
+  const uint32_t* off_span;
+  const uint32_t* len;
+  const uint32_t* chunk_first;
+  const int32_t* carry_in;
+  cmb_contig_stats* rows;
+  uint32_t tid_begin, n_local, n_chunks, excl;
+  uint32_t* ticket;
+  int32_t* arena;
+  uint2* rec;
+  uint32_t rec_capacity;
+  uint32_t* rec_count;
+  uint2* warp_table;  // [n_chunks * 16] {offset, count}
+  uint4* ovf;         // {contig_local, depth, count, 0}
+  uint32_t ovf_capacity;
+  uint32_t* ovf_count;
+  uint32_t* error_flags;
+};
+
+constexpr uint32_t K2_SMEM_STAGE_BYTES = K2_STAGES * CHUNK_BYTES;
+constexpr uint32_t K2_SMEM_MISC = 64 /*barriers + tickets*/ + 2 * K2_WARPS * 8 /*warp aggregates, double-buffered*/;
+constexpr uint32_t K2_SMEM_BYTES_HIST = K2_SMEM_STAGE_BYTES + K2_SMEM_MISC + 2 * HIST_TOTAL * 4;
+constexpr uint32_t K2_SMEM_BYTES_NOHIST = K2_SMEM_STAGE_BYTES + K2_SMEM_MISC;
+
+template <bool HIST, bool CLEAN>
+__global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_constant__ CUtensorMap tmap, const K2Args a) {
+  extern __shared__ __align__(1024) uint8_t smem[];  // stage tiles need the 1024 B swizzle-atom alignment
+  uint64_t* full = reinterpret_cast<uint64_t*>(smem + K2_SMEM_STAGE_BYTES);
+  uint32_t* s_chunk = reinterpret_cast<uint32_t*>(full + K2_STAGES);
+  int2* wagg2 = reinterpret_cast<int2*>(smem + K2_SMEM_STAGE_BYTES + 64);
+  uint32_t* hist2 = reinterpret_cast<uint32_t*>(wagg2 + 2 * K2_WARPS);
+
+  const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
+
+  auto issue = [&](uint32_t s) {  // thread 0: claim the next chunk and start its TMA load into stage s
+    const uint32_t tk = atomicAdd(a.ticket, 1u);
+    s_chunk[s] = tk;
+    if (tk < a.n_chunks) {
+      const uint32_t bar = smem_u32(full + s);
+      mbar_arrive_expect_tx(bar, CHUNK_BYTES);
+      tma_load_2d(smem_u32(smem + s * CHUNK_BYTES), &tmap, 0, (int32_t)(tk * CHUNK_ROWS), bar);
+    }
+  };
+
+  // flush one histogram buffer: warp w owns slot w/4, bins (w%4)*128 .. +128 -> sorted (depth,count) records
+  auto flush_hist = [&](uint32_t* hist, uint32_t chunk, int base0) {
+    const uint32_t fslot = warp >> 2;
+    const uint32_t bin0 = (warp & 3) * 128 + lane;
+    uint32_t cnt[4], msk[4], total = 0;
+#pragma unroll
+    for (uint32_t k = 0; k < 4; ++k) {
+      cnt[k] = hist[fslot * HIST_BINS + bin0 + 32 * k];
+      msk[k] = __ballot_sync(FULL, cnt[k] != 0);
+      total += __popc(msk[k]);
+    }
+    uint32_t base = 0;
+    if (total) {
+      if (lane == 0) base = atomicAdd(a.rec_count, total);
+      base = __shfl_sync(FULL, base, 0);
+      const bool fits = (uint64_t)base + total <= a.rec_capacity;
+      if (!fits && lane == 0) atomicOr(a.error_flags, ERR_CAPACITY);
+      uint32_t before = 0;
+      const int fb = fslot == 0 ? base0 : 0;
+#pragma unroll
+      for (uint32_t k = 0; k < 4; ++k) {
+        if (cnt[k]) {
+          if (fits) a.rec[base + before + __popc(msk[k] & ((1u << lane) - 1))] = make_uint2((uint32_t)(fb + (int)(bin0 + 32 * k)), cnt[k]);
+          hist[fslot * HIST_BINS + bin0 + 32 * k] = 0;
+        }
+        before += __popc(msk[k]);
+      }
+      if (!fits) total = 0;
+    }
+    if (lane == 0) a.warp_table[(uint64_t)chunk * K2_WARPS + warp] = make_uint2(base, total);
+  };
+
+  if (t == 0) {
+    for (uint32_t s = 0; s < K2_STAGES; ++s) mbar_init(smem_u32(full + s), 1);
+    fence_barrier_init();
+  }
+  if (HIST)
+    for (uint32_t b = t; b < 2 * HIST_TOTAL; b += K2_THREADS) hist2[b] = 0;
+  __syncthreads();
+  if (t == 0)
+    for (uint32_t s = 0; s < K2_STAGES; ++s) issue(s);
+  __syncthreads();
+
+  const uint32_t row = t >> 1, half = t & 1;
+  const uint32_t E = a.excl;
+  uint32_t prev_chunk = 0;
+  int prev_base0 = 0;
+  uint32_t it = 0;
+
+  for (;; ++it) {
+    const uint32_t s = it % K2_STAGES;
+    const uint32_t chunk = s_chunk[s];
+    if (chunk >= a.n_chunks) break;
+    int2* wagg = wagg2 + (it & 1) * K2_WARPS;
+    uint32_t* hist = hist2 + (it & 1) * HIST_TOTAL;
+    mbar_wait(smem_u32(full + s), (it / K2_STAGES) & 1);
+
+    // ---- 16 consecutive elements per thread: 4 x LDS.128 through the 128B swizzle (conflict-free)
+    int v[SPAN];
+    {
+      const uint8_t* rowp = smem + s * CHUNK_BYTES + row * 128;
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j) {
+        const uint32_t unit = (half * 4 + j) ^ (row & 7);
+        const int4 q = *reinterpret_cast<const int4*>(rowp + unit * 16);
+        v[4 * j + 0] = q.x;
+        v[4 * j + 1] = q.y;
+        v[4 * j + 2] = q.z;
+        v[4 * j + 3] = q.w;
+      }
+    }
+    const uint32_t span = chunk * CHUNK_SPANS + t;
+    if (CLEAN) {  // re-zero only the 16 B units that hold an event (the arena is zero everywhere else)
+      int4* g = reinterpret_cast<int4*>(a.arena + (uint64_t)span * SPAN);
+#pragma unroll
+      for (uint32_t j = 0; j < 4; ++j)
+        if (v[4 * j] | v[4 * j + 1] | v[4 * j + 2] | v[4 * j + 3]) g[j] = make_int4(0, 0, 0, 0);
+    }
+
+    // ---- which contig owns this span
+    const uint32_t cf = __ldg(a.chunk_first + chunk);
+    uint32_t lo = cf, hi = __ldg(a.chunk_first + chunk + 1);
+    while (lo < hi) {
+      const uint32_t mid = (lo + hi + 1) >> 1;
+      if (__ldg(a.off_span + mid) <= span) lo = mid;
+      else hi = mid - 1;
+    }
+    const uint32_t c = lo;
+    const uint32_t cstart = __ldg(a.off_span + c);
+    const uint32_t L = __ldg(a.len + c);
+    const bool is_head = span == cstart;
+    const uint32_t rel = (span - cstart) * SPAN;  // position in the contig of v[0]
+    const uint32_t n_in = rel >= L ? 0u : min(SPAN, L - rel);
+    uint32_t w0 = 0, w1 = 0;
+    if (2ull * E < L) {
+      const uint32_t ws = E, we = L - E;
+      w0 = rel >= ws ? 0u : min(SPAN, ws - rel);
+      w1 = rel >= we ? 0u : min(SPAN, we - rel);
+      if (w1 < w0) w1 = w0;
+    }
+
+    // ---- thread-local inclusive prefix
+#pragma unroll
+    for (uint32_t j = 1; j < SPAN; ++j) v[j] += v[j - 1];
+
+    // ---- segmented (by contig head) inclusive scan of span totals across the warp
+    int val = v[SPAN - 1];
+    int flg = is_head;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const int ov = __shfl_up_sync(FULL, val, d);
+      const int of = __shfl_up_sync(FULL, flg, d);
+      if ((int)lane >= d) {
+        if (!flg) val += ov;
+        flg |= of;
+      }
+    }
+    int pval = __shfl_up_sync(FULL, val, 1), pflg = __shfl_up_sync(FULL, flg, 1);
+    if (lane == 0) {
+      pval = 0;
+      pflg = 0;
+    }
+    if (lane == 31) wagg[warp] = make_int2(val, flg);
+    __syncthreads();  // stage fully read; warp aggregates visible; the previous chunk's histogram adds are complete
+    if (t == 0) issue(s);
+    if (HIST && it > 0) flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk, prev_base0);
+
+    int wv, wf;
+    {
+      const int2 wa = lane < K2_WARPS ? wagg[lane] : make_int2(0, 0);
+      wv = wa.x;
+      wf = wa.y;
+#pragma unroll
+      for (int d = 1; d < (int)K2_WARPS; d <<= 1) {
+        const int ov = __shfl_up_sync(FULL, wv, d);
+        const int of = __shfl_up_sync(FULL, wf, d);
+        if ((int)lane >= d) {
+          if (!wf) wv += ov;
+          wf |= of;
+        }
+      }
+      const int src = warp ? (int)warp - 1 : 0;
+      wv = __shfl_sync(FULL, wv, src);
+      wf = __shfl_sync(FULL, wf, src);
+      if (warp == 0) {
+        wv = 0;
+        wf = 0;
+      }
+    }
+    const int cin = __ldg(a.carry_in + chunk);
+    int carry;
+    if (is_head) carry = 0;
+    else if (pflg) carry = pval;
+    else if (wf) carry = wv + pval;
+    else carry = cin + wv + pval;
+
+    // ---- reductions over this span (EST:393-404, 447-465, 494-501), run by run
+    uint32_t cov_full = 0, cov_win = 0;
+    uint64_t sum_win = 0;
+    const uint32_t slot = c - cf;
+    const int base0 = max(0, cin - (int)(HIST_BINS / 2));
+    const int hbase = slot == 0 ? base0 : 0;
+    auto hist_add = [&](int depth, uint32_t cnt) {
+      const int b = depth - hbase;
+      if (depth < 0) {  // impossible for a consistent arena (every -1 follows its +1 within the contig)
+        atomicOr(a.error_flags, ERR_INTERNAL);
+      } else if (slot < HIST_SLOTS && (uint32_t)b < HIST_BINS) {
+        atomicAdd(hist + slot * HIST_BINS + b, cnt);
+      } else {  // rare: more than HIST_SLOTS contigs in the chunk, or depth outside the window
+        const uint32_t o = atomicAdd(a.ovf_count, 1u);
+        if (o < a.ovf_capacity) a.ovf[o] = make_uint4(c, (uint32_t)depth, cnt, 0);
+        else atomicOr(a.error_flags, ERR_CAPACITY);
+        atomicOr(&a.rows[a.tid_begin + c].reserved, ROWFLAG_OVF);
+      }
+    };
+    const bool inw = (w1 - w0) == SPAN;                            // the whole span lies in the end-trimmed window
+    const bool whole = n_in == SPAN && (inw || w1 == w0);           // no contig end / window edge inside the span
+    bool uniform = false;                                           // constant depth over the span (no event)
+    if (whole) {
+      int pv = 0;         // prefix value of the open run: its depth is carry + pv
+      uint32_t start = 0;
+      auto close_run = [&](uint32_t end) {
+        const uint32_t n = end - start;
+        if (n) {
+          const int depth = carry + pv;
+          const uint32_t cn = depth > 0 ? n : 0u;
+          cov_full += cn;
+          if (inw) {
+            cov_win += cn;
+            sum_win += (uint64_t)(uint32_t)depth * n;
+            if (HIST) hist_add(depth, n);
+          }
+        }
+      };
+#pragma unroll
+      for (uint32_t j = 0; j < SPAN; ++j) {
+        if (v[j] != pv) {  // a delta at j: the open run ends here
+          close_run(j);
+          pv = v[j];
+          start = j;
+        }
+      }
+      if (start == 0 && pv == v[0] && v[SPAN - 1] == v[0] && pv == 0) {
+        uniform = true;  // never left the initial run: handled below, warp-aggregated
+        const uint32_t cn = carry > 0 ? SPAN : 0u;
+        cov_full += cn;
+        if (inw) {
+          cov_win += cn;
+          sum_win += (uint64_t)(uint32_t)carry * SPAN;
+        }
+      } else {
+        close_run(SPAN);
+      }
+    } else {  // contig end or window edge inside the span (two or three spans per contig): element by element
+      int run_depth = 0;
+      uint32_t run_cnt = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < SPAN; ++j) {
+        const int d = carry + v[j];
+        const bool in_c = j < n_in, in_w = j >= w0 && j < w1;
+        cov_full += (in_c && d > 0);
+        cov_win += (in_w && d > 0);
+        if (in_w) sum_win += (uint64_t)(int64_t)d;
+        if (HIST && in_w) {
+          if (run_cnt && d == run_depth) {
+            ++run_cnt;
+          } else {
+            if (run_cnt) hist_add(run_depth, run_cnt);
+            run_depth = d;
+            run_cnt = 1;
+          }
+        }
+      }
+      if (HIST && run_cnt) hist_add(run_depth, run_cnt);
+    }
+    if (HIST) {
+      // event-free spans of the window: aggregate the lanes that agree with the first such lane into one shared atomic
+      const bool cand = uniform && inw;
+      const uint32_t cm = __ballot_sync(FULL, cand);
+      if (cm) {
+        const int leader = __ffs(cm) - 1;
+        const int d0 = __shfl_sync(FULL, carry, leader);
+        const uint32_t c0 = __shfl_sync(FULL, c, leader);
+        const bool same = cand && carry == d0 && c == c0;
+        const uint32_t m = __ballot_sync(FULL, same);
+        if (same) {
+          if ((int)lane == leader) hist_add(carry, SPAN * (uint32_t)__popc(m));
+        } else if (cand) {
+          hist_add(carry, SPAN);
+        }
+      }
+    }
+
+    // ---- per-contig accumulation: one RED triple per (warp, contig)
+    {
+      const uint32_t c0 = __shfl_sync(FULL, c, 0);
+      if (__all_sync(FULL, c == c0)) {
+        const uint32_t sf = __reduce_add_sync(FULL, cov_full), sw = __reduce_add_sync(FULL, cov_win);
+        const uint64_t sd = warp_sum_u64(sum_win);
+        if (lane == 0) {
+          cmb_contig_stats* rowp = a.rows + a.tid_begin + c0;
+          if (sf) atomicAdd((unsigned long long*)&rowp->covered_full, (unsigned long long)sf);
+          if (sw) atomicAdd((unsigned long long*)&rowp->covered_window, (unsigned long long)sw);
+          if (sd) atomicAdd((unsigned long long*)&rowp->sum_depth_window, (unsigned long long)sd);
+        }
+      } else {
+        cmb_contig_stats* rowp = a.rows + a.tid_begin + c;
+        if (cov_full) atomicAdd((unsigned long long*)&rowp->covered_full, (unsigned long long)cov_full);
+        if (cov_win) atomicAdd((unsigned long long*)&rowp->covered_window, (unsigned long long)cov_win);
+        if (sum_win) atomicAdd((unsigned long long*)&rowp->sum_depth_window, (unsigned long long)sum_win);
+      }
+    }
+    prev_chunk = chunk;
+    prev_base0 = base0;
+  }
+  if (HIST && it > 0) {
+    __syncthreads();  // the last chunk's histogram adds
+    flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk, prev_base0);
+  }
+}
