@@ -11,9 +11,12 @@ constexpr uint32_t ROW_ELEMS = 32;              // TMA row: 32 x i32 = 128 B
 constexpr uint32_t CHUNK_ROWS = CHUNK / ROW_ELEMS;  // 256
 constexpr uint32_t K2_STAGES = 3;
 constexpr uint32_t K2_WARPS = K2_THREADS / 32;  // 16
-constexpr uint32_t HIST_SLOTS = 4;              // contigs per chunk with a shared-memory histogram
-constexpr uint32_t HIST_BINS = 512;             // bins per slot
-constexpr uint32_t HIST_TOTAL = HIST_SLOTS * HIST_BINS;  // 2048 = 16 warps x 128
+constexpr uint32_t HIST_SLOTS = 16;             // contigs per chunk with a shared-memory histogram (one per K2 warp)
+constexpr uint32_t HIST_BINS = 128;             // direct-mapped bins per slot: bin = depth % 128, word = tag|count
+constexpr uint32_t HIST_TOTAL = HIST_SLOTS * HIST_BINS;  // 2048
+constexpr uint32_t HIST_CNT_BITS = 14;          // a chunk holds 8192 = 2^13 positions, so a count fits 14 bits
+constexpr uint32_t HIST_MAX_DEPTH = ((1u << (32 - HIST_CNT_BITS)) - 2) * HIST_BINS;  // deeper runs use the overflow list
+constexpr uint32_t OVF_NIL = 0xffffffffu;
 constexpr uint32_t K1_THREADS = 256;
 constexpr uint32_t ROWFLAG_OVF = 1u;            // cmb_contig_stats.reserved: some records are in the overflow list
 

@@ -86,6 +86,7 @@ struct cmb_ctx {
   uint32_t rec_capacity = 0;
   uint2* d_warp_table = nullptr;
   uint4* d_ovf = nullptr;
+  uint32_t* d_ovf_head = nullptr;
   uint32_t ovf_capacity = 0;
   cmb_hist_pair* d_pairs = nullptr;
   uint64_t pair_capacity = 0;
@@ -184,6 +185,8 @@ void free_reference(cmb_ctx* c) {
   cudaFree(c->d_rec);
   cudaFree(c->d_warp_table);
   cudaFree(c->d_ovf);
+  cudaFree(c->d_ovf_head);
+  c->d_ovf_head = nullptr;
   cudaFree(c->d_pairs);
   c->d_arena = nullptr;
   c->d_off_span = c->d_len = c->d_chunk_first = nullptr;
@@ -277,8 +280,9 @@ int run_end_of_sample(cmb_ctx* c) {
   a.rows = c->d_rows; a.tid_begin = c->tid_begin; a.n_local = c->n_local; a.n_chunks = c->n_chunks; a.excl = excl;
   a.ticket = c->d_counters + 1; a.arena = c->d_arena;
   a.rec = c->d_rec; a.rec_capacity = c->rec_capacity; a.rec_count = c->d_counters + 2;
-  a.warp_table = c->d_warp_table; a.ovf = c->d_ovf; a.ovf_capacity = c->ovf_capacity; a.ovf_count = c->d_counters + 3;
+  a.warp_table = c->d_warp_table; a.ovf = c->d_ovf; a.ovf_head = c->d_ovf_head; a.ovf_capacity = c->ovf_capacity; a.ovf_count = c->d_counters + 3;
   a.error_flags = c->d_counters + 0;
+  if (hist) CU_TRY(c, cudaMemsetAsync(c->d_ovf_head, 0xff, 4ull * c->n_chunks, c->stream));
   CU_TRY(c, cudaEventRecord(c->ev[3], c->stream));
   int rc;
   if (hist) rc = c->clean_as_you_go ? launch_k2_variant<true, true>(c, a) : launch_k2_variant<true, false>(c, a);
@@ -292,7 +296,7 @@ int run_end_of_sample(cmb_ctx* c) {
     k.off_span = c->d_off_span; k.len = c->d_len; k.chunk_first = c->d_chunk_first; k.rows = c->d_rows;
     k.tid_begin = c->tid_begin; k.n_local = c->n_local; k.excl = excl;
     k.trim_min = c->params.trim_min; k.trim_max = c->params.trim_max;
-    k.rec = c->d_rec; k.warp_table = c->d_warp_table; k.ovf = c->d_ovf; k.ovf_count = c->d_counters + 3;
+    k.rec = c->d_rec; k.warp_table = c->d_warp_table; k.ovf = c->d_ovf; k.ovf_head = c->d_ovf_head;
     k.ovf_capacity = c->ovf_capacity;
     k.pairs = c->d_pairs; k.pair_count = (unsigned long long*)(c->d_counters + 4); k.pair_capacity = c->pair_capacity;
     k.want_csr = csr; k.error_flags = c->d_counters + 0;
@@ -488,6 +492,7 @@ int cmb_set_reference(cmb_ctx* c, uint32_t n_contigs, const uint64_t* contig_len
   CU_TRY(c, cudaMalloc(&c->d_rec, 8ull * c->rec_capacity));
   CU_TRY(c, cudaMalloc(&c->d_warp_table, 8ull * c->n_chunks * K2_WARPS));
   CU_TRY(c, cudaMalloc(&c->d_ovf, 16ull * c->ovf_capacity));
+  CU_TRY(c, cudaMalloc(&c->d_ovf_head, 4ull * c->n_chunks));
   c->arena_dirty = true;
   // TMA descriptor: the arena as [rows][32] i32, box = one chunk (256 rows x 128 B), 128B swizzle
   PFN_encodeTiled encode = nullptr;

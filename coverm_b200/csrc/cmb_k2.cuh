@@ -6,8 +6,8 @@
 // so a span never straddles two contigs.  Running depth at a span = chunk carry (K1b) + segmented warp/CTA scan of the
 // span totals.  Depth is piecewise constant, so everything is accumulated per RUN (a run ends where a delta is
 // non-zero, ~1-2 % of positions): covered bases, sum of depth, and the depth histogram of the end-trimmed window, which
-// lives in shared memory per (contig slot, depth bin) and is flushed as (depth,count) records while the next chunk is
-// being scanned (double-buffered, so the chunk loop has a single __syncthreads).
+// lives in shared memory per (contig slot, depth % 128) with the high depth bits as a tag, and is flushed as
+// (depth,count) records while the next chunk is being scanned (double-buffered: one __syncthreads per chunk).
 #pragma once
 
 struct K2Args {
@@ -23,7 +23,8 @@ struct K2Args {
   uint32_t rec_capacity;
   uint32_t* rec_count;
   uint2* warp_table;  // [n_chunks * 16] {offset, count}
-  uint4* ovf;         // {contig_local, depth, count, 0}
+  uint4* ovf;         // {contig_local, depth, count, next} — per-chunk linked lists
+  uint32_t* ovf_head; // [n_chunks] list heads (OVF_NIL = empty)
   uint32_t ovf_capacity;
   uint32_t* ovf_count;
   uint32_t* error_flags;
@@ -54,15 +55,13 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     }
   };
 
-  // flush one histogram buffer: warp w owns slot w/4, bins (w%4)*128 .. +128 -> sorted (depth,count) records
-  auto flush_hist = [&](uint32_t* hist, uint32_t chunk, int base0) {
-    const uint32_t fslot = warp >> 2;
-    const uint32_t bin0 = (warp & 3) * 128 + lane;
-    uint32_t cnt[4], msk[4], total = 0;
+  // flush one histogram buffer: warp w owns contig slot w (128 bins, 4 per lane) -> (depth,count) records
+  auto flush_hist = [&](uint32_t* hist, uint32_t chunk) {
+    uint32_t word[4], msk[4], total = 0;
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {
-      cnt[k] = hist[fslot * HIST_BINS + bin0 + 32 * k];
-      msk[k] = __ballot_sync(FULL, cnt[k] != 0);
+      word[k] = hist[warp * HIST_BINS + lane + 32 * k];
+      msk[k] = __ballot_sync(FULL, word[k] != 0);
       total += __popc(msk[k]);
     }
     uint32_t base = 0;
@@ -72,12 +71,12 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
       const bool fits = (uint64_t)base + total <= a.rec_capacity;
       if (!fits && lane == 0) atomicOr(a.error_flags, ERR_CAPACITY);
       uint32_t before = 0;
-      const int fb = fslot == 0 ? base0 : 0;
 #pragma unroll
       for (uint32_t k = 0; k < 4; ++k) {
-        if (cnt[k]) {
-          if (fits) a.rec[base + before + __popc(msk[k] & ((1u << lane) - 1))] = make_uint2((uint32_t)(fb + (int)(bin0 + 32 * k)), cnt[k]);
-          hist[fslot * HIST_BINS + bin0 + 32 * k] = 0;
+        if (word[k]) {
+          const uint32_t depth = ((word[k] >> HIST_CNT_BITS) - 1) * HIST_BINS + lane + 32 * k;
+          if (fits) a.rec[base + before + __popc(msk[k] & ((1u << lane) - 1))] = make_uint2(depth, word[k] & ((1u << HIST_CNT_BITS) - 1));
+          hist[warp * HIST_BINS + lane + 32 * k] = 0;
         }
         before += __popc(msk[k]);
       }
@@ -100,7 +99,6 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
   const uint32_t row = t >> 1, half = t & 1;
   const uint32_t E = a.excl;
   uint32_t prev_chunk = 0;
-  int prev_base0 = 0;
   uint32_t it = 0;
 
   for (;; ++it) {
@@ -179,7 +177,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     if (lane == 31) wagg[warp] = make_int2(val, flg);
     __syncthreads();  // stage fully read; warp aggregates visible; the previous chunk's histogram adds are complete
     if (t == 0) issue(s);
-    if (HIST && it > 0) flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk, prev_base0);
+    if (HIST && it > 0) flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk);
 
     int wv, wf;
     {
@@ -214,19 +212,33 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     uint32_t cov_full = 0, cov_win = 0;
     uint64_t sum_win = 0;
     const uint32_t slot = c - cf;
-    const int base0 = max(0, cin - (int)(HIST_BINS / 2));
-    const int hbase = slot == 0 ? base0 : 0;
     auto hist_add = [&](int depth, uint32_t cnt) {
-      const int b = depth - hbase;
+      // direct-mapped bin (depth % 128) holding (depth / 128 + 1) << 14 | count: conflict-free while the depths of one
+      // contig inside one chunk span < 128 values, wherever that range sits
       if (depth < 0) {  // impossible for a consistent arena (every -1 follows its +1 within the contig)
         atomicOr(a.error_flags, ERR_INTERNAL);
-      } else if (slot < HIST_SLOTS && (uint32_t)b < HIST_BINS) {
-        atomicAdd(hist + slot * HIST_BINS + b, cnt);
-      } else {  // rare: more than HIST_SLOTS contigs in the chunk, or depth outside the window
+        return;
+      }
+      bool done = false;
+      if (slot < HIST_SLOTS && (uint32_t)depth < HIST_MAX_DEPTH) {
+        uint32_t* w = hist + slot * HIST_BINS + ((uint32_t)depth & (HIST_BINS - 1));
+        const uint32_t tag = ((uint32_t)depth / HIST_BINS) + 1;
+        uint32_t cur = *(volatile uint32_t*)w;
+        if (cur == 0) cur = atomicCAS(w, 0u, (tag << HIST_CNT_BITS) | cnt);
+        if (cur == 0) done = true;  // we installed tag and count
+        else if ((cur >> HIST_CNT_BITS) == tag) {
+          atomicAdd(w, cnt);
+          done = true;
+        }
+      }
+      if (!done) {  // > 16 contigs in the chunk, or two depths 128 apart in one chunk: per-chunk overflow list
         const uint32_t o = atomicAdd(a.ovf_count, 1u);
-        if (o < a.ovf_capacity) a.ovf[o] = make_uint4(c, (uint32_t)depth, cnt, 0);
-        else atomicOr(a.error_flags, ERR_CAPACITY);
-        atomicOr(&a.rows[a.tid_begin + c].reserved, ROWFLAG_OVF);
+        if (o < a.ovf_capacity) {
+          const uint32_t next = atomicExch(a.ovf_head + chunk, o);
+          a.ovf[o] = make_uint4(c, (uint32_t)depth, cnt, next);
+        } else {
+          atomicOr(a.error_flags, ERR_CAPACITY);
+        }
       }
     };
     const bool inw = (w1 - w0) == SPAN;                            // the whole span lies in the end-trimmed window
@@ -327,10 +339,9 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
       }
     }
     prev_chunk = chunk;
-    prev_base0 = base0;
   }
   if (HIST && it > 0) {
     __syncthreads();  // the last chunk's histogram adds
-    flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk, prev_base0);
+    flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk);
   }
 }

@@ -1,8 +1,8 @@
 // K3: per-contig histogram finalisation, one WARP per contig.
 //
-// K2 left, per (chunk, warp), a short list of (depth,count) records, ascending in depth, for the contig slot that warp
-// flushes.  A contig gathers the lists of the chunks it overlaps into a per-warp shared-memory window of depth bins
-// [dmin, dmin+512) (repeated for deeper windows if ever needed), then walks the bins in order with warp scans:
+// K2 left, per (chunk, contig slot), a short list of (depth,count) records (plus, rarely, records on the chunk's
+// overflow list).  A contig gathers the lists of the chunks it overlaps into a per-warp shared-memory window of depth
+// bins [dmin, dmin+512) (repeated for deeper windows if ever needed), then walks the bins in order with warp scans:
 //   * trimmed-mean `total` exactly as the reference's ascending walk (EST:598-642),
 //   * S0 = sum n, S1 = sum x n, S2 = sum x^2 n (wrapping u64) and k = lowest depth -> variance sums (EST:790-805),
 //   * optionally the merged (depth,count) pairs (CSR) for the host-side per-genome merge / coverage_histogram.
@@ -22,7 +22,7 @@ struct K3Args {
   const uint2* rec;
   const uint2* warp_table;
   const uint4* ovf;
-  const uint32_t* ovf_count;
+  const uint32_t* ovf_head;
   uint32_t ovf_capacity;
   cmb_hist_pair* pairs;
   unsigned long long* pair_count;
@@ -47,29 +47,36 @@ __global__ void __launch_bounds__(K3_THREADS) k3_finalize(const K3Args a) {
   const uint64_t min_index = (uint64_t)floorf(__fmul_rn(a.trim_min, Tf));
   const uint64_t max_index = (uint64_t)ceilf(__fmul_rn(a.trim_max, Tf));
   const uint32_t k0 = a.off_span[lc] / CHUNK_SPANS, k1 = (a.off_span[lc + 1] - 1) / CHUNK_SPANS;
-  const uint32_t n_ent = (k1 - k0 + 1) * 4;
-  const bool has_ovf = row->reserved & ROWFLAG_OVF;
-  const uint32_t n_ovf = has_ovf ? min(*a.ovf_count, a.ovf_capacity) : 0;
+  const uint32_t n_chunk = k1 - k0 + 1;
 
-  // ---- depth range of this contig's records (each list is ascending: first / last record)
+  // Visits every record of this contig: the (chunk, slot) lists one after the other with the records lane-parallel,
+  // then the chunks' overflow lists (one lane per chunk).
+  auto for_each_record = [&](auto&& fn) {
+    for (uint32_t i = 0; i < n_chunk; ++i) {
+      const uint32_t k = k0 + i;
+      const uint32_t slot = lc - a.chunk_first[k];
+      if (slot >= HIST_SLOTS) continue;
+      const uint2 ent = a.warp_table[(uint64_t)k * K2_WARPS + slot];
+      for (uint32_t r = lane; r < ent.y; r += 32) {
+        const uint2 rc = a.rec[ent.x + r];
+        fn(rc.x, rc.y);
+      }
+    }
+    for (uint32_t i = lane; i < n_chunk; i += 32) {
+      for (uint32_t o = a.ovf_head[k0 + i]; o != OVF_NIL && o < a.ovf_capacity;) {
+        const uint4 rc = a.ovf[o];
+        if (rc.x == lc) fn(rc.y, rc.z);
+        o = rc.w;
+      }
+    }
+  };
+
+  // ---- depth range of this contig's records
   uint32_t dmin = 0xffffffffu, dmax = 0;
-  for (uint32_t e = lane; e < n_ent; e += 32) {
-    const uint32_t k = k0 + (e >> 2);
-    const uint32_t slot = lc - a.chunk_first[k];
-    if (slot >= HIST_SLOTS) continue;
-    const uint2 ent = a.warp_table[(uint64_t)k * K2_WARPS + slot * 4 + (e & 3)];
-    if (ent.y) {
-      dmin = min(dmin, a.rec[ent.x].x);
-      dmax = max(dmax, a.rec[ent.x + ent.y - 1].x);
-    }
-  }
-  for (uint32_t o = lane; o < n_ovf; o += 32) {
-    const uint4 rc = a.ovf[o];
-    if (rc.x == lc) {
-      dmin = min(dmin, rc.y);
-      dmax = max(dmax, rc.y);
-    }
-  }
+  for_each_record([&](uint32_t depth, uint32_t) {
+    dmin = min(dmin, depth);
+    dmax = max(dmax, depth);
+  });
   dmin = __reduce_min_sync(FULL, dmin);
   dmax = __reduce_max_sync(FULL, dmax);
   if (dmin > dmax) return;  // no records (cannot happen for a contig with a window)
@@ -85,22 +92,10 @@ __global__ void __launch_bounds__(K3_THREADS) k3_finalize(const K3Args a) {
       const uint32_t nb = min(K3_WINDOW, dmax - wbase + 1);
       for (uint32_t b = lane; b < nb; b += 32) whist[b] = 0;
       __syncwarp();
-      for (uint32_t e = 0; e < n_ent; ++e) {  // lists one after the other, records lane-parallel
-        const uint32_t k = k0 + (e >> 2);
-        const uint32_t slot = lc - a.chunk_first[k];
-        if (slot >= HIST_SLOTS) continue;
-        const uint2 ent = a.warp_table[(uint64_t)k * K2_WARPS + slot * 4 + (e & 3)];
-        for (uint32_t r = lane; r < ent.y; r += 32) {
-          const uint2 rc = a.rec[ent.x + r];
-          const uint32_t b = rc.x - wbase;
-          if (rc.x >= wbase && b < nb) atomicAdd(&whist[b], rc.y);
-        }
-      }
-      for (uint32_t o = lane; o < n_ovf; o += 32) {
-        const uint4 rc = a.ovf[o];
-        const uint32_t b = rc.y - wbase;
-        if (rc.x == lc && rc.y >= wbase && b < nb) atomicAdd(&whist[b], rc.z);
-      }
+      for_each_record([&](uint32_t depth, uint32_t cnt) {
+        const uint32_t b = depth - wbase;
+        if (depth >= wbase && b < nb) atomicAdd(&whist[b], cnt);
+      });
       __syncwarp();
       for (uint32_t b0 = 0; b0 < nb; b0 += 32) {
         const uint32_t b = b0 + lane;
