@@ -4,10 +4,12 @@
 // 3-stage ring of 32 KB tiles in flight with TMA (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx).  A
 // thread owns one 16-element span (4 x LDS.128, conflict-free through the swizzle); contigs start on span boundaries,
 // so a span never straddles two contigs.  Running depth at a span = chunk carry (K1b) + segmented warp/CTA scan of the
-// span totals.  Depth is piecewise constant, so everything is accumulated per RUN (a run ends where a delta is
-// non-zero, ~1-2 % of positions): covered bases, sum of depth, and the depth histogram of the end-trimmed window, which
-// lives in shared memory per (contig slot, depth % 128) with the high depth bits as a tag, and is flushed as
-// (depth,count) records while the next chunk is being scanned (double-buffered: one __syncthreads per chunk).
+// span totals.  Depth is piecewise constant and deltas are sparse (~1-2 % of positions), so a thread only keeps the
+// span total and a 16-bit mask of its non-zero positions; covered bases, sum of depth and the depth histogram of the
+// end-trimmed window are then accumulated per RUN in a short loop over the set bits (the deltas are re-read from the
+// shared-memory tile, which stays resident until the next iteration's barrier).  The histogram lives in shared memory
+// per (contig slot, depth % 128) with the high depth bits as a tag, and is flushed as (depth,count) records while the
+// next chunk is being scanned (double-buffered: one __syncthreads per chunk).
 #pragma once
 
 struct K2Args {
@@ -22,7 +24,7 @@ struct K2Args {
   uint2* rec;
   uint32_t rec_capacity;
   uint32_t* rec_count;
-  uint2* warp_table;  // [n_chunks * 16] {offset, count}
+  uint2* warp_table;  // [n_chunks * 16] {offset, count}: records of contig slot w of the chunk
   uint4* ovf;         // {contig_local, depth, count, next} — per-chunk linked lists
   uint32_t* ovf_head; // [n_chunks] list heads (OVF_NIL = empty)
   uint32_t ovf_capacity;
@@ -56,7 +58,8 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
   };
 
   // flush one histogram buffer: warp w owns contig slot w (128 bins, 4 per lane) -> (depth,count) records
-  auto flush_hist = [&](uint32_t* hist, uint32_t chunk) {
+  auto flush_hist = [&](uint32_t* hist, uint32_t chunk, uint32_t n_slots) {
+    if (warp >= n_slots) return;  // this chunk has fewer contigs than warps
     uint32_t word[4], msk[4], total = 0;
 #pragma unroll
     for (uint32_t k = 0; k < 4; ++k) {
@@ -98,7 +101,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
 
   const uint32_t row = t >> 1, half = t & 1;
   const uint32_t E = a.excl;
-  uint32_t prev_chunk = 0;
+  uint32_t prev_chunk = 0, prev_slots = 0;
   uint32_t it = 0;
 
   for (;; ++it) {
@@ -109,31 +112,29 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     uint32_t* hist = hist2 + (it & 1) * HIST_TOTAL;
     mbar_wait(smem_u32(full + s), (it / K2_STAGES) & 1);
 
-    // ---- 16 consecutive elements per thread: 4 x LDS.128 through the 128B swizzle (conflict-free)
-    int v[SPAN];
+    // ---- 16 consecutive deltas per thread: 4 x LDS.128 through the 128B swizzle (conflict-free).
+    //      Only their sum and the mask of non-zero positions stay in registers.
+    const uint8_t* rowp = smem + s * CHUNK_BYTES + row * 128;
+    const uint32_t span = chunk * CHUNK_SPANS + t;
+    int total = 0;
+    uint32_t ev = 0;
     {
-      const uint8_t* rowp = smem + s * CHUNK_BYTES + row * 128;
+      int4* g = reinterpret_cast<int4*>(a.arena + (uint64_t)span * SPAN);
 #pragma unroll
       for (uint32_t j = 0; j < 4; ++j) {
         const uint32_t unit = (half * 4 + j) ^ (row & 7);
         const int4 q = *reinterpret_cast<const int4*>(rowp + unit * 16);
-        v[4 * j + 0] = q.x;
-        v[4 * j + 1] = q.y;
-        v[4 * j + 2] = q.z;
-        v[4 * j + 3] = q.w;
+        const uint32_t e4 = (q.x != 0 ? 1u : 0u) | (q.y != 0 ? 2u : 0u) | (q.z != 0 ? 4u : 0u) | (q.w != 0 ? 8u : 0u);
+        total += (q.x + q.y) + (q.z + q.w);
+        ev |= e4 << (4 * j);
+        if (CLEAN && e4) g[j] = make_int4(0, 0, 0, 0);  // re-zero only the 16 B units that hold an event
       }
-    }
-    const uint32_t span = chunk * CHUNK_SPANS + t;
-    if (CLEAN) {  // re-zero only the 16 B units that hold an event (the arena is zero everywhere else)
-      int4* g = reinterpret_cast<int4*>(a.arena + (uint64_t)span * SPAN);
-#pragma unroll
-      for (uint32_t j = 0; j < 4; ++j)
-        if (v[4 * j] | v[4 * j + 1] | v[4 * j + 2] | v[4 * j + 3]) g[j] = make_int4(0, 0, 0, 0);
     }
 
     // ---- which contig owns this span
     const uint32_t cf = __ldg(a.chunk_first + chunk);
-    uint32_t lo = cf, hi = __ldg(a.chunk_first + chunk + 1);
+    const uint32_t cl = __ldg(a.chunk_first + chunk + 1);
+    uint32_t lo = cf, hi = cl;
     while (lo < hi) {
       const uint32_t mid = (lo + hi + 1) >> 1;
       if (__ldg(a.off_span + mid) <= span) lo = mid;
@@ -143,7 +144,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     const uint32_t cstart = __ldg(a.off_span + c);
     const uint32_t L = __ldg(a.len + c);
     const bool is_head = span == cstart;
-    const uint32_t rel = (span - cstart) * SPAN;  // position in the contig of v[0]
+    const uint32_t rel = (span - cstart) * SPAN;  // position in the contig of the span's first element
     const uint32_t n_in = rel >= L ? 0u : min(SPAN, L - rel);
     uint32_t w0 = 0, w1 = 0;
     if (2ull * E < L) {
@@ -153,12 +154,8 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
       if (w1 < w0) w1 = w0;
     }
 
-    // ---- thread-local inclusive prefix
-#pragma unroll
-    for (uint32_t j = 1; j < SPAN; ++j) v[j] += v[j - 1];
-
     // ---- segmented (by contig head) inclusive scan of span totals across the warp
-    int val = v[SPAN - 1];
+    int val = total;
     int flg = is_head;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -175,9 +172,11 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
       pflg = 0;
     }
     if (lane == 31) wagg[warp] = make_int2(val, flg);
-    __syncthreads();  // stage fully read; warp aggregates visible; the previous chunk's histogram adds are complete
-    if (t == 0) issue(s);
-    if (HIST && it > 0) flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk);
+    __syncthreads();  // warp aggregates visible; the previous iteration's tile and histogram adds are complete
+    if (it > 0) {
+      if (t == 0) issue((it - 1) % K2_STAGES);  // refill the tile of the previous iteration (read until this barrier)
+      if (HIST) flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk, prev_slots);
+    }
 
     int wv, wf;
     {
@@ -241,69 +240,44 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
         }
       }
     };
-    const bool inw = (w1 - w0) == SPAN;                            // the whole span lies in the end-trimmed window
-    const bool whole = n_in == SPAN && (inw || w1 == w0);           // no contig end / window edge inside the span
-    bool uniform = false;                                           // constant depth over the span (no event)
-    if (whole) {
-      int pv = 0;         // prefix value of the open run: its depth is carry + pv
-      uint32_t start = 0;
-      auto close_run = [&](uint32_t end) {
-        const uint32_t n = end - start;
-        if (n) {
-          const int depth = carry + pv;
-          const uint32_t cn = depth > 0 ? n : 0u;
-          cov_full += cn;
-          if (inw) {
-            cov_win += cn;
-            sum_win += (uint64_t)(uint32_t)depth * n;
-            if (HIST) hist_add(depth, n);
-          }
-        }
-      };
-#pragma unroll
-      for (uint32_t j = 0; j < SPAN; ++j) {
-        if (v[j] != pv) {  // a delta at j: the open run ends here
-          close_run(j);
-          pv = v[j];
-          start = j;
-        }
+    // a run [from, to) of the span at one depth, clipped to the contig and to its end-trimmed window
+    auto close_run = [&](int depth, uint32_t from, uint32_t to) {
+      const uint32_t nc = min(to, n_in) - min(from, n_in);
+      const uint32_t nw = min(max(to, w0), w1) - min(max(from, w0), w1);
+      if (depth > 0) {
+        cov_full += nc;
+        cov_win += nw;
       }
-      if (start == 0 && pv == v[0] && v[SPAN - 1] == v[0] && pv == 0) {
-        uniform = true;  // never left the initial run: handled below, warp-aggregated
-        const uint32_t cn = carry > 0 ? SPAN : 0u;
-        cov_full += cn;
-        if (inw) {
-          cov_win += cn;
-          sum_win += (uint64_t)(uint32_t)carry * SPAN;
-        }
-      } else {
-        close_run(SPAN);
+      if (nw) {
+        sum_win += (uint64_t)(int64_t)depth * nw;
+        if (HIST) hist_add(depth, nw);
       }
-    } else {  // contig end or window edge inside the span (two or three spans per contig): element by element
-      int run_depth = 0;
-      uint32_t run_cnt = 0;
-#pragma unroll
-      for (uint32_t j = 0; j < SPAN; ++j) {
-        const int d = carry + v[j];
-        const bool in_c = j < n_in, in_w = j >= w0 && j < w1;
-        cov_full += (in_c && d > 0);
-        cov_win += (in_w && d > 0);
-        if (in_w) sum_win += (uint64_t)(int64_t)d;
-        if (HIST && in_w) {
-          if (run_cnt && d == run_depth) {
-            ++run_cnt;
-          } else {
-            if (run_cnt) hist_add(run_depth, run_cnt);
-            run_depth = d;
-            run_cnt = 1;
-          }
-        }
+    };
+    if (ev) {
+      int depth = carry;
+      uint32_t from = 0;
+      uint32_t m = ev;
+      while (m) {
+        const uint32_t j = (uint32_t)__ffs(m) - 1;
+        m &= m - 1;
+        close_run(depth, from, j);
+        const uint32_t unit = (half * 4 + (j >> 2)) ^ (row & 7);
+        depth += *reinterpret_cast<const int*>(rowp + unit * 16 + (j & 3) * 4);  // the delta at position j
+        from = j;
       }
-      if (HIST && run_cnt) hist_add(run_depth, run_cnt);
+      close_run(depth, from, SPAN);
+    } else {  // no event in the span: constant depth
+      const uint32_t nc = n_in, nw = w1 - w0;
+      if (carry > 0) {
+        cov_full += nc;
+        cov_win += nw;
+      }
+      sum_win += (uint64_t)(int64_t)carry * nw;
     }
     if (HIST) {
-      // event-free spans of the window: aggregate the lanes that agree with the first such lane into one shared atomic
-      const bool cand = uniform && inw;
+      // event-free spans: aggregate the lanes that agree with the first such lane into one shared-memory atomic
+      const uint32_t nw = w1 - w0;
+      const bool cand = ev == 0 && nw > 0;
       const uint32_t cm = __ballot_sync(FULL, cand);
       if (cm) {
         const int leader = __ffs(cm) - 1;
@@ -312,9 +286,10 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
         const bool same = cand && carry == d0 && c == c0;
         const uint32_t m = __ballot_sync(FULL, same);
         if (same) {
-          if ((int)lane == leader) hist_add(carry, SPAN * (uint32_t)__popc(m));
+          const uint32_t tot = __reduce_add_sync(m, nw);
+          if ((int)lane == leader) hist_add(carry, tot);
         } else if (cand) {
-          hist_add(carry, SPAN);
+          hist_add(carry, nw);
         }
       }
     }
@@ -326,22 +301,23 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
         const uint32_t sf = __reduce_add_sync(FULL, cov_full), sw = __reduce_add_sync(FULL, cov_win);
         const uint64_t sd = warp_sum_u64(sum_win);
         if (lane == 0) {
-          cmb_contig_stats* rowp = a.rows + a.tid_begin + c0;
-          if (sf) atomicAdd((unsigned long long*)&rowp->covered_full, (unsigned long long)sf);
-          if (sw) atomicAdd((unsigned long long*)&rowp->covered_window, (unsigned long long)sw);
-          if (sd) atomicAdd((unsigned long long*)&rowp->sum_depth_window, (unsigned long long)sd);
+          cmb_contig_stats* rowp2 = a.rows + a.tid_begin + c0;
+          if (sf) atomicAdd((unsigned long long*)&rowp2->covered_full, (unsigned long long)sf);
+          if (sw) atomicAdd((unsigned long long*)&rowp2->covered_window, (unsigned long long)sw);
+          if (sd) atomicAdd((unsigned long long*)&rowp2->sum_depth_window, (unsigned long long)sd);
         }
       } else {
-        cmb_contig_stats* rowp = a.rows + a.tid_begin + c;
-        if (cov_full) atomicAdd((unsigned long long*)&rowp->covered_full, (unsigned long long)cov_full);
-        if (cov_win) atomicAdd((unsigned long long*)&rowp->covered_window, (unsigned long long)cov_win);
-        if (sum_win) atomicAdd((unsigned long long*)&rowp->sum_depth_window, (unsigned long long)sum_win);
+        cmb_contig_stats* rowp2 = a.rows + a.tid_begin + c;
+        if (cov_full) atomicAdd((unsigned long long*)&rowp2->covered_full, (unsigned long long)cov_full);
+        if (cov_win) atomicAdd((unsigned long long*)&rowp2->covered_window, (unsigned long long)cov_win);
+        if (sum_win) atomicAdd((unsigned long long*)&rowp2->sum_depth_window, (unsigned long long)sum_win);
       }
     }
     prev_chunk = chunk;
+    prev_slots = cl - cf + 1;
   }
   if (HIST && it > 0) {
     __syncthreads();  // the last chunk's histogram adds
-    flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk);
+    flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk, prev_slots);
   }
 }
