@@ -70,8 +70,8 @@ struct cmb_ctx {
   std::vector<DevBatch> dev_batch;
   std::vector<cudaEvent_t> batch_done;
   std::vector<bool> batch_busy;
-  int acquired = -1;
-  uint32_t next_batch = 0;
+  uint32_t n_acquired = 0;   // staging batches handed out and not yet submitted (FIFO)
+  uint32_t next_batch = 0;   // next staging slot to hand out
   // reference
   uint32_t n_contigs = 0, tid_begin = 0, tid_end = 0, n_local = 0;
   uint64_t arena_elems = 0;
@@ -555,31 +555,31 @@ int cmb_begin_sample(cmb_ctx* c) {
   }
   c->in_sample = true;
   c->ended = false;
-  c->acquired = -1;
+  c->n_acquired = 0;
   return CMB_OK;
 }
 
 int cmb_acquire_batch(cmb_ctx* c, cmb_read_batch* batch) {
   if (!c || !batch) return fail(c, CMB_E_ARG, "cmb_acquire_batch: null argument");
   if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_acquire_batch: no sample in progress");
-  if (c->acquired >= 0) return fail(c, CMB_E_ARG, "cmb_acquire_batch: previous batch not submitted");
+  if (c->n_acquired >= c->cfg.n_staging) return fail(c, CMB_E_ARG, "cmb_acquire_batch: every staging batch is already acquired");
   const uint32_t i = c->next_batch;
-  if (c->batch_busy[i]) {
+  if (c->batch_busy[i]) {  // its previous H2D + K1 must have drained
     CU_TRY(c, cudaEventSynchronize(c->batch_done[i]));
     c->batch_busy[i] = false;
   }
   *batch = c->host_batch[i];
-  c->acquired = (int)i;
+  c->next_batch = (i + 1) % c->cfg.n_staging;
+  c->n_acquired += 1;
   return CMB_OK;
 }
 
 int cmb_submit_batch(cmb_ctx* c, uint32_t n_records, uint32_t n_intervals) {
   if (!c) return CMB_E_ARG;
-  if (!c->in_sample || c->acquired < 0) return fail(c, CMB_E_ARG, "cmb_submit_batch: no acquired batch");
+  if (!c->in_sample || c->n_acquired == 0) return fail(c, CMB_E_ARG, "cmb_submit_batch: no acquired batch");
   if (n_records > c->cfg.batch_records || n_intervals > c->cfg.batch_intervals) return fail(c, CMB_E_ARG, "cmb_submit_batch: batch exceeds capacity");
-  const uint32_t i = (uint32_t)c->acquired;
-  c->acquired = -1;
-  c->next_batch = (i + 1) % c->cfg.n_staging;
+  const uint32_t i = (c->next_batch + c->cfg.n_staging - c->n_acquired) % c->cfg.n_staging;  // oldest acquired batch
+  c->n_acquired -= 1;
   if (n_records == 0) return CMB_OK;
   if (c->n_local == 0) return CMB_OK;
   const cmb_read_batch& h = c->host_batch[i];
@@ -620,7 +620,7 @@ int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* dev, uint32_t n_re
 int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** dev_stats) {
   if (!c) return CMB_E_ARG;
   if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_end_sample: no sample in progress");
-  if (c->acquired >= 0) return fail(c, CMB_E_ARG, "cmb_end_sample: an acquired batch was not submitted");
+  if (c->n_acquired) return fail(c, CMB_E_ARG, "cmb_end_sample: an acquired batch was not submitted");
   CU_TRY(c, cudaSetDevice(c->device));
   c->in_sample = false;
   if (c->n_local) {

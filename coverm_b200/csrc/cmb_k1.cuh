@@ -209,6 +209,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
     for (uint32_t k = ivb; k < ive; ++k) {
       const int32_t s = a.iv_start[k];
       const uint32_t n = (uint32_t)a.iv_len[k];
+      if (s == INT_MIN) continue;  // CMB_IV_PAD: unused slot of the interval pool
       if (s < 0 || (uint32_t)s >= L) {  // `ups_and_downs[cursor] += 1` would panic
         err |= ERR_BOUNDS;
         continue;

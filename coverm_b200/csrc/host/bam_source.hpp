@@ -160,6 +160,10 @@ class InflateStream {
     return true;
   }
   uint64_t compressed_bytes() const { return n_; }
+  // uncompressed / fully inflated inputs: the raw byte range (BlockIndex cuts it into slices)
+  bool is_raw() const { return kind_ == RAW; }
+  const uint8_t* raw_data() const { return raw_p_; }
+  size_t raw_size() const { return raw_n_; }
 
  private:
   struct Block {

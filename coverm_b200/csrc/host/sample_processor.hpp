@@ -6,6 +6,7 @@
 #include <cstdio>
 
 #include "bam_source.hpp"
+#include "decode_pipeline.hpp"
 
 namespace cmbh {
 
@@ -168,15 +169,17 @@ class SamToBam {
 class DeviceSession {
  public:
   DeviceSession(int device, int threads, uint32_t batch_records = 1u << 20) : pool_(threads) {
+    if (const char* e = getenv("CMB_BATCH_RECORDS")) batch_records = std::max(40000u, (uint32_t)strtoul(e, nullptr, 10));
     cmb_device_cfg cfg{};
     cfg.device = device;
     cfg.batch_records = batch_records;
     cfg.batch_intervals = batch_records + batch_records / 2;
-    cfg.n_staging = 3;
+    cfg.n_staging = 4;
     int rc = cmb_create(&cfg, &ctx_);
     if (rc != CMB_OK) throw ExitError(1, std::string("cannot create the CUDA coverage context: ") + cmb_last_error(nullptr));
     batch_records_ = cfg.batch_records;
     batch_intervals_ = cfg.batch_intervals;
+    n_staging_ = cfg.n_staging;
   }
   ~DeviceSession() { cmb_destroy(ctx_); }
   DeviceSession(const DeviceSession&) = delete;
@@ -199,7 +202,13 @@ class DeviceSession {
       p = sam_as_bam.data();
       n = sam_as_bam.size();
     }
-    InflateStream stream(p, n, pool_, 48u << 20);
+    int rc;
+    cmb_filter_mode mode{};
+    rc = cmb_set_params(ctx_, &params, &mode);
+    if (rc) throw_device_error(ctx_, rc);
+    const bool pair_mode = mode.filter_pairs;
+    // pair mode decodes window by window (mate matching is sequential); otherwise only the header is read here
+    InflateStream stream(p, n, pool_, pair_mode ? (48u << 20) : (1u << 20));
     std::vector<uint8_t> buf;
     size_t begin = 0;  // first unconsumed byte of buf
     auto need = [&](size_t bytes_needed) {  // make buf[begin, begin+bytes_needed) available; false at EOF
@@ -228,19 +237,16 @@ class DeviceSession {
       res.header.lens.push_back(rd_u32(buf.data() + begin + o + 4 + l_name));
       o += 8 + l_name;
     }
+    const uint64_t records_at = o;  // uncompressed offset of the first record (nothing has been discarded yet)
     begin += o;
 
     // ---- device reference + params
-    int rc;
     const uint32_t sb = std::min<uint32_t>(shard_begin_, n_ref), se = std::min<uint32_t>(shard_end_, n_ref);
     if (res.header.lens != ref_lens_) {
       rc = cmb_set_reference(ctx_, n_ref, res.header.lens.data(), sb, se);
       if (rc) throw_device_error(ctx_, rc);
       ref_lens_ = res.header.lens;
     }
-    cmb_filter_mode mode{};
-    rc = cmb_set_params(ctx_, &params, &mode);
-    if (rc) throw_device_error(ctx_, rc);
     rc = cmb_begin_sample(ctx_);
     if (rc) throw_device_error(ctx_, rc);
 
@@ -266,7 +272,6 @@ class DeviceSession {
       if (r2) throw_device_error(ctx_, r2);
       have_batch = false;
     };
-    const bool pair_mode = mode.filter_pairs;
     std::vector<size_t> rec_off;
     constexpr size_t ITEM = 4096;  // records per parallel work item
     struct ItemOut {
@@ -295,7 +300,28 @@ class DeviceSession {
       }
     };
 
-    for (;;) {
+    if (!pair_mode) {
+      // region-parallel pipeline (decode_pipeline.hpp): this thread only acquires / submits staging batches
+      BlockIndex bx;
+      if (stream.is_raw()) bx.build(stream.raw_data(), stream.raw_size());
+      else bx.build(p, n);
+      const PipelineCounts pc = run_decode_pipeline(
+          bx, records_at, pool_.size(), batch_records_, batch_intervals_, n_staging_,
+          [&](cmb_read_batch* b) {
+            const double a = now_s();
+            int r2 = cmb_acquire_batch(ctx_, b);
+            wait_s += now_s() - a;
+            if (r2) throw_device_error(ctx_, r2);
+          },
+          [&](uint32_t nr, uint32_t ni) {
+            const double a = now_s();
+            int r2 = cmb_submit_batch(ctx_, nr, ni);
+            wait_s += now_s() - a;
+            if (r2) throw_device_error(ctx_, r2);
+          });
+      res.n_records = pc.n_records;
+      res.num_detected_primary_alignments = pc.primaries;
+    } else for (;;) {
       // complete records currently in buf
       rec_off.clear();
       size_t q = begin;
@@ -319,49 +345,7 @@ class DeviceSession {
       if (items.size() < n_items) items.resize(n_items);
       if (max_iv > batch_intervals_) throw ExitError(1, "a window of records has more aligned blocks than a device batch holds");
 
-      if (!pair_mode) {
-        if (have_batch && (used_r + nrec > batch_records_ || used_i + max_iv > batch_intervals_)) submit();
-        if (!have_batch) acquire();
-        const uint32_t r_base = used_r;
-        const uint8_t* base = buf.data();
-        pool_.parallel_for(n_items, [&](size_t it, int) {
-          ItemOut& io = items[it];
-          io.iv_start.clear();
-          io.iv_len.clear();
-          io.primaries = 0;
-          const size_t r0 = it * ITEM, r1 = std::min(nrec, r0 + ITEM);
-          Tuple t;
-          for (size_t r = r0; r < r1; ++r) {
-            const uint32_t before = (uint32_t)io.iv_start.size();
-            decode_bam_record(base + rec_off[r], t, io.iv_start, io.iv_len);
-            const uint32_t i = r_base + (uint32_t)r;
-            batch.tid[i] = t.tid; batch.pos[i] = t.pos; batch.flag[i] = t.flag; batch.mapq[i] = t.mapq;
-            batch.nm_state[i] = t.nm_state; batch.nm[i] = t.nm; batch.l_seq[i] = t.l_seq; batch.aligned[i] = t.aligned;
-            batch.del[i] = t.del; batch.ins[i] = t.ins;
-            batch.iv_begin[i] = before;  // item-local; rebased below
-            if (!(t.flag & 0x900)) ++io.primaries;
-          }
-        });
-        // rebase interval offsets (items are in record order)
-        std::vector<uint32_t> item_base(n_items);
-        uint32_t acc = used_i;
-        for (size_t it = 0; it < n_items; ++it) {
-          item_base[it] = acc;
-          acc += (uint32_t)items[it].iv_start.size();
-          res.num_detected_primary_alignments += items[it].primaries;
-        }
-        pool_.parallel_for(n_items, [&](size_t it, int) {
-          const ItemOut& io = items[it];
-          const size_t r0 = it * ITEM, r1 = std::min(nrec, r0 + ITEM);
-          for (size_t r = r0; r < r1; ++r) batch.iv_begin[r_base + r] += item_base[it];
-          if (!io.iv_start.empty()) {
-            memcpy(batch.iv_start + item_base[it], io.iv_start.data(), 4 * io.iv_start.size());
-            memcpy(batch.iv_len + item_base[it], io.iv_len.data(), 4 * io.iv_len.size());
-          }
-        });
-        used_r += (uint32_t)nrec;
-        used_i = acc;
-      } else {
+      {
         // filter.rs:117-233: decode in parallel, then match mates in stream order; only completed pairs reach the GPU
         tuples.resize(nrec);
         std::vector<uint32_t> iv_at(nrec);
@@ -433,7 +417,7 @@ class DeviceSession {
  private:
   ThreadPool pool_;
   cmb_ctx* ctx_ = nullptr;
-  uint32_t batch_records_ = 0, batch_intervals_ = 0;
+  uint32_t batch_records_ = 0, batch_intervals_ = 0, n_staging_ = 0;
   uint32_t shard_begin_ = 0, shard_end_ = 0xffffffffu;
   std::vector<uint64_t> ref_lens_;
 };

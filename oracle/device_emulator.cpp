@@ -20,7 +20,7 @@ struct cmb_ctx {
   cmb_device_cfg cfg{};
   std::vector<std::vector<uint8_t>> slabs;
   std::vector<cmb_read_batch> batches;
-  int acquired = -1;
+  uint32_t n_acquired = 0;
   uint32_t next = 0;
   std::vector<uint64_t> lens;
   uint32_t tid_begin = 0, tid_end = 0;
@@ -100,11 +100,14 @@ int cmb_begin_sample(cmb_ctx* c) {
   c->in_sample = true;
   c->ended = false;
   c->n_records = c->n_intervals = 0;
+  c->n_acquired = 0;
   return CMB_OK;
 }
 int cmb_acquire_batch(cmb_ctx* c, cmb_read_batch* b) {
+  if (c->n_acquired >= c->cfg.n_staging) return fail(c, CMB_E_ARG, "cmb_acquire_batch: every staging batch is already acquired");
   *b = c->batches[c->next];
-  c->acquired = (int)c->next;
+  c->next = (c->next + 1) % c->cfg.n_staging;
+  c->n_acquired += 1;
   return CMB_OK;
 }
 
@@ -174,6 +177,7 @@ static int submit(cmb_ctx* c, const cmb_read_batch& b, uint32_t n, uint32_t ni) 
     const uint64_t L = c->lens[tid];
     for (uint32_t k = b.iv_begin[i]; k < b.iv_begin[i + 1]; ++k) {
       const int32_t s = b.iv_start[k];
+      if (s == CMB_IV_PAD) continue;
       if (s < 0 || (uint64_t)s >= L) { c->error |= 4; continue; }
       ud[s] += 1;
       const uint64_t e = (uint64_t)s + (uint32_t)b.iv_len[k];
@@ -186,9 +190,9 @@ static int submit(cmb_ctx* c, const cmb_read_batch& b, uint32_t n, uint32_t ni) 
 }
 
 int cmb_submit_batch(cmb_ctx* c, uint32_t n, uint32_t ni) {
-  const int i = c->acquired;
-  c->acquired = -1;
-  c->next = (uint32_t)(i + 1) % c->cfg.n_staging;
+  if (c->n_acquired == 0) return fail(c, CMB_E_ARG, "cmb_submit_batch: no acquired batch");
+  const uint32_t i = (c->next + c->cfg.n_staging - c->n_acquired) % c->cfg.n_staging;
+  c->n_acquired -= 1;
   return submit(c, c->batches[i], n, ni);
 }
 int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* b, uint32_t n, uint32_t ni) { return submit(c, *b, n, ni); }
