@@ -12,6 +12,7 @@
 // Replaces for this path: bam::Reader::read + htslib's BGZF thread pool (bam_generator.rs:103-134, 125-129).
 #pragma once
 #include <atomic>
+#include <chrono>
 #include <climits>
 #include <exception>
 #include <memory>
@@ -166,256 +167,6 @@ inline uint32_t decode_bam_record_into(const uint8_t* rec, Tuple& t, int32_t* iv
     a += sz;
   }
   return n_iv;
-}
-
-struct PipelineCounts {
-  uint64_t n_records = 0, primaries = 0;
-};
-
-// Runs the whole record stream (starting at uncompressed offset `records_at`) through the device context.
-// acquire()/submit() are the caller's wrappers around cmb_acquire_batch / cmb_submit_batch (called only from this thread).
-template <class Acquire, class Submit>
-PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, int n_threads, uint32_t cap_r, uint32_t cap_i,
-                                   uint32_t n_staging, Acquire acquire, Submit submit) {
-  constexpr size_t ITEM_BYTES = 1u << 20;
-  struct Item { size_t b0, b1; };
-  std::vector<Item> items;
-  size_t first_block = 0;
-  while (first_block < bx.blocks.size() && bx.ustart[first_block + 1] <= records_at) ++first_block;
-  const uint64_t skip0 = first_block < bx.blocks.size() ? records_at - bx.ustart[first_block] : 0;
-  size_t max_item = 0;
-  for (size_t b = first_block; b < bx.blocks.size();) {
-    size_t e = b;
-    uint64_t sz = 0;
-    while (e < bx.blocks.size() && (sz == 0 || sz + bx.blocks[e].isize <= ITEM_BYTES)) sz += bx.blocks[e++].isize;
-    items.push_back({b, e});
-    max_item = std::max<size_t>(max_item, sz);
-    b = e;
-  }
-  const size_t n_items = items.size();
-
-  struct Chain {  // state handed from item i-1 to item i
-    std::atomic<int> ready{0};
-    std::vector<uint8_t> carry;  // bytes of the record that straddles the boundary
-    uint64_t batch_seq = 0;
-    uint32_t used_r = 0, used_i = 0;
-    uint32_t items_in_batch = 0;  // items with records assigned to batch_seq so far
-  };
-  std::unique_ptr<Chain[]> chain(new Chain[n_items + 1]);
-  chain[0].ready.store(1);
-
-  struct Slot {  // one staging batch in flight
-    std::atomic<int64_t> have_seq{-1};  // batch sequence number whose pointers are published here
-    cmb_read_batch ptrs{};
-    std::atomic<uint32_t> done{0};      // items of this batch fully extracted
-    std::atomic<int> closed{0};
-    uint32_t final_r = 0, final_i = 0, final_items = 0;
-  };
-  std::unique_ptr<Slot[]> slots(new Slot[n_staging]);
-  std::atomic<int64_t> needed_seq{0};
-  std::atomic<size_t> next_item{0};
-  std::atomic<bool> abort{false};
-  std::atomic<int> workers_left{0};
-  std::exception_ptr first_error;
-  std::mutex err_mu;
-  std::atomic<uint64_t> tot_records{0}, tot_primaries{0};
-
-  auto fail = [&](std::exception_ptr e) {
-    std::lock_guard<std::mutex> g(err_mu);
-    if (!first_error) first_error = e;
-    abort = true;
-  };
-
-  auto worker = [&]() {
-    try {
-      z_stream zs;
-      memset(&zs, 0, sizeof zs);
-      if (inflateInit2(&zs, -15) != Z_OK) throw Panic("zlib init failed");
-      std::unique_ptr<uint8_t[]> buf(new uint8_t[max_item + 8]);
-      std::vector<uint32_t> offs;
-      std::vector<uint8_t> stitched;
-      uint64_t my_records = 0, my_primaries = 0;
-      for (;;) {
-        const size_t i = next_item.fetch_add(1);
-        if (i >= n_items || abort) break;
-        const Item& it = items[i];
-        const size_t usize = (size_t)(bx.ustart[it.b1] - bx.ustart[it.b0]);
-        bx.inflate(it.b0, it.b1, buf.get(), &zs);
-        while (!chain[i].ready.load(std::memory_order_acquire)) {
-          if (abort) break;
-          std::this_thread::yield();
-        }
-        if (abort) break;
-        // ---- alignment: finish the straddling record, then walk my records
-        Chain& in = chain[i];
-        Chain& out = chain[i + 1];
-        size_t pos = i == 0 ? (size_t)skip0 : 0;
-        bool have_stitched = false;
-        offs.clear();
-        uint64_t ub_iv = 0;
-        bool swallowed = false;  // the whole item is the middle of one huge record
-        if (!in.carry.empty()) {
-          stitched = std::move(in.carry);
-          while (stitched.size() < 4 && pos < usize) stitched.push_back(buf[pos++]);
-          if (stitched.size() < 4) {
-            swallowed = true;
-          } else {
-            const size_t need = 4 + (size_t)rd_u32(stitched.data());
-            if (need < 36) throw Panic("Error reading BAM record: corrupt block_size");
-            const size_t take = std::min(need - stitched.size(), usize - pos);
-            stitched.insert(stitched.end(), buf.get() + pos, buf.get() + pos + take);
-            pos += take;
-            if (stitched.size() < need) swallowed = true;
-            else {
-              have_stitched = true;
-              ub_iv += rd_u16(stitched.data() + 4 + 12);
-            }
-          }
-        }
-        if (swallowed) {
-          out.carry = std::move(stitched);
-        } else {
-          while (pos + 4 <= usize) {
-            const uint32_t bs = rd_u32(buf.get() + pos);
-            if (bs < 32) throw Panic("Error reading BAM record: corrupt block_size");
-            if (pos + 4 + (size_t)bs > usize) break;
-            offs.push_back((uint32_t)pos);
-            ub_iv += rd_u16(buf.get() + pos + 4 + 12);
-            pos += 4 + (size_t)bs;
-          }
-          out.carry.assign(buf.get() + pos, buf.get() + usize);
-        }
-        const uint32_t n_rec = (uint32_t)offs.size() + (have_stitched ? 1u : 0u);
-        if (n_rec > cap_r || ub_iv > cap_i) throw ExitError(1, "a decode work item holds more records than a device batch");
-        // ---- batch assignment
-        uint64_t seq = in.batch_seq;
-        uint32_t used_r = in.used_r, used_i = in.used_i, items_in_batch = in.items_in_batch;
-        auto wait_for_slot = [&](uint64_t q) {  // until the coordinator has handed staging memory to batch q
-          while (slots[q % n_staging].have_seq.load(std::memory_order_acquire) != (int64_t)q) {
-            if (abort) return false;
-            std::this_thread::yield();
-          }
-          return true;
-        };
-        if (used_r + (uint64_t)n_rec > cap_r || used_i + ub_iv > cap_i) {  // close the current batch, open the next
-          if (!wait_for_slot(seq)) break;
-          Slot& s = slots[seq % n_staging];
-          s.final_r = used_r;
-          s.final_i = used_i;
-          s.final_items = items_in_batch;
-          s.closed.store(1, std::memory_order_release);
-          ++seq;
-          used_r = used_i = items_in_batch = 0;
-          int64_t cur = needed_seq.load();
-          while (cur < (int64_t)seq && !needed_seq.compare_exchange_weak(cur, (int64_t)seq)) {
-          }
-        }
-        out.batch_seq = seq;
-        out.used_r = used_r + n_rec;
-        out.used_i = used_i + (uint32_t)ub_iv;
-        out.items_in_batch = items_in_batch + (n_rec ? 1u : 0u);
-        out.ready.store(1, std::memory_order_release);
-        if (!n_rec) continue;
-        // ---- extraction into the staging batch
-        if (!wait_for_slot(seq)) break;
-        Slot& slot = slots[seq % n_staging];
-        const cmb_read_batch& b = slot.ptrs;
-        uint32_t r = used_r, iv = used_i;
-        Tuple t;
-        auto put = [&](const uint8_t* rec) {
-          const uint32_t n_iv = decode_bam_record_into(rec, t, b.iv_start + iv, b.iv_len + iv);
-          b.tid[r] = t.tid; b.pos[r] = t.pos; b.flag[r] = t.flag; b.mapq[r] = t.mapq; b.nm_state[r] = t.nm_state;
-          b.nm[r] = t.nm; b.l_seq[r] = t.l_seq; b.aligned[r] = t.aligned; b.del[r] = t.del; b.ins[r] = t.ins;
-          b.iv_begin[r] = iv;
-          iv += n_iv;
-          ++r;
-          if (!(t.flag & 0x900)) ++my_primaries;
-        };
-        if (have_stitched) put(stitched.data());
-        for (uint32_t o : offs) put(buf.get() + o);
-        for (const uint32_t end_iv = used_i + (uint32_t)ub_iv; iv < end_iv; ++iv) {  // unused part of my interval reservation
-          b.iv_start[iv] = CMB_IV_PAD;
-          b.iv_len[iv] = 0;
-        }
-        my_records += n_rec;
-        slot.done.fetch_add(1, std::memory_order_acq_rel);
-      }
-      inflateEnd(&zs);
-      tot_records += my_records;
-      tot_primaries += my_primaries;
-    } catch (...) {
-      fail(std::current_exception());
-    }
-    workers_left.fetch_sub(1);
-  };
-
-  const int nt = std::max(1, std::min<int>(n_threads, (int)std::max<size_t>(1, n_items)));
-  workers_left = nt;
-  std::vector<std::thread> pool;
-  for (int k = 0; k < nt; ++k) pool.emplace_back(worker);
-
-  // ---- coordinator: the only thread that touches the device ABI
-  int64_t acquired = 0, submitted = 0;
-  try {
-    for (;;) {
-      bool progressed = false;
-      while (acquired <= needed_seq.load() && acquired - submitted < (int64_t)n_staging) {
-        Slot& s = slots[acquired % n_staging];
-        s.closed.store(0);
-        s.done.store(0);
-        acquire(&s.ptrs);
-        s.have_seq.store(acquired, std::memory_order_release);
-        ++acquired;
-        progressed = true;
-      }
-      if (submitted < acquired) {
-        Slot& s = slots[submitted % n_staging];
-        if (s.closed.load(std::memory_order_acquire) && s.done.load(std::memory_order_acquire) == s.final_items) {
-          s.ptrs.iv_begin[s.final_r] = s.final_i;
-          submit(s.final_r, s.final_i);
-          ++submitted;
-          progressed = true;
-        }
-      }
-      if (abort) break;
-      if (workers_left.load() == 0 && !progressed) {
-        bool more = false;  // workers are done: is a closed batch still waiting, or one still to acquire?
-        if (submitted < acquired && slots[submitted % n_staging].closed.load()) more = true;
-        if (acquired <= needed_seq.load() && acquired - submitted < (int64_t)n_staging) more = true;
-        if (!more) break;
-      }
-      if (!progressed) std::this_thread::yield();
-    }
-  } catch (...) {
-    fail(std::current_exception());
-  }
-  for (auto& th : pool) th.join();
-  if (first_error) {
-    // hand back every acquired batch so that the context can be reused
-    try {
-      for (; submitted < acquired; ++submitted) submit(0, 0);
-    } catch (...) {
-    }
-    std::rethrow_exception(first_error);
-  }
-  // ---- the last, still open batch (and any batch acquired ahead but never used)
-  const Chain& fin = chain[n_items];
-  for (; submitted < acquired; ++submitted) {
-    Slot& s = slots[submitted % n_staging];
-    if ((uint64_t)submitted == fin.batch_seq && !s.closed.load()) {
-      s.ptrs.iv_begin[fin.used_r] = fin.used_i;
-      submit(fin.used_r, fin.used_i);
-    } else if (s.closed.load()) {
-      s.ptrs.iv_begin[s.final_r] = s.final_i;
-      submit(s.final_r, s.final_i);
-    } else {
-      submit(0, 0);
-    }
-  }
-  PipelineCounts c;
-  c.n_records = tot_records;
-  c.primaries = tot_primaries;
-  return c;
 }
 
 }  // namespace cmbh

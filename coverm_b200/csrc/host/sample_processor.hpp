@@ -6,7 +6,7 @@
 #include <cstdio>
 
 #include "bam_source.hpp"
-#include "decode_pipeline.hpp"
+#include "decode_runner.hpp"
 
 namespace cmbh {
 
@@ -301,7 +301,7 @@ class DeviceSession {
     };
 
     if (!pair_mode) {
-      // region-parallel pipeline (decode_pipeline.hpp): this thread only acquires / submits staging batches
+      // region-parallel pipeline (decode_runner.hpp): this thread only acquires / submits staging batches
       BlockIndex bx;
       if (stream.is_raw()) bx.build(stream.raw_data(), stream.raw_size());
       else bx.build(p, n);
@@ -321,6 +321,9 @@ class DeviceSession {
           });
       res.n_records = pc.n_records;
       res.num_detected_primary_alignments = pc.primaries;
+      if (getenv("CMB_PIPELINE_STATS"))
+        fprintf(stderr, "#pipeline\titems=%u\tworkers=%u\tinflate_s=%.3f\tchain_s=%.3f\textract_s=%.3f\tidle_s=%.3f (summed over workers)\n",
+                pc.n_items, pc.n_workers, pc.inflate_s, pc.scan_s, pc.extract_s, pc.idle_s);
     } else for (;;) {
       // complete records currently in buf
       rec_off.clear();
