@@ -3,9 +3,12 @@
 // Work items are ~1 MB of uncompressed data (whole BGZF blocks).  Three kinds of work, none of which ever blocks on
 // another thread:
 //   INFLATE(item)   any worker, any order: zlib-inflate the item's blocks into a pooled buffer.
+//                   While the data is hot in its cache the same worker GUESSES where the first whole record of the
+//                   item starts (a chain of plausible BAM record headers) and pre-walks the block_size chain from there.
 //   CHAIN           whoever gets the try-lock: for every consecutive inflated item, finish the record that straddles
-//                   the item boundary, walk the block_size chain (one load per record — the only sequential work,
-//                   ~5 ns/record), assign the item a contiguous slice of a staging batch, queue it for extraction.
+//                   the item boundary — which gives the exact start — and, if the guess was right (it practically
+//                   always is), take the pre-walked offsets; otherwise walk the chain now.  Then assign the item a
+//                   contiguous slice of a staging batch and queue it for extraction.  O(1) per item, exact always.
 //   EXTRACT(item)   any worker: decode the item's records straight into the pinned SoA staging batch.
 // The calling thread is the coordinator: it alone talks to the (not thread-safe) device ABI — it keeps one staging
 // batch acquired ahead of the chain and submits each batch once every item assigned to it has been extracted.
@@ -31,8 +34,8 @@ inline double pipeline_now() {
 // Runs the whole record stream (starting at uncompressed offset `records_at`) through the device context.
 // acquire()/submit() are the caller's wrappers around cmb_acquire_batch / cmb_submit_batch (called only from this thread).
 template <class Acquire, class Submit>
-PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, int n_threads, uint32_t cap_r, uint32_t cap_i,
-                                   uint32_t n_staging, Acquire acquire, Submit submit) {
+PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, uint32_t n_ref, int n_threads, uint32_t cap_r,
+                                   uint32_t cap_i, uint32_t n_staging, Acquire acquire, Submit submit) {
   constexpr size_t ITEM_BYTES = 1u << 20;
   struct WorkCtx {  // pooled per-item scratch
     std::unique_ptr<uint8_t[]> buf;
@@ -43,6 +46,10 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, in
     size_t b0 = 0, b1 = 0, usize = 0;
     std::atomic<int> inflated{0};
     int ctx = -1;
+    // speculative alignment, set by the inflating worker
+    int64_t guess_start = -1;
+    size_t guess_tail = 0;      // offset of the incomplete last record
+    uint64_t guess_ub_iv = 0;
     // set by the chain step
     bool have_stitched = false;
     uint64_t seq = 0;
@@ -76,7 +83,7 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, in
   const int nt = std::max(1, std::min<int>(n_threads, (int)std::max<size_t>(1, n_items)));
 
   // ---- pooled contexts (bounds memory: 3 buffers per worker)
-  const int n_ctx = nt * 3;
+  const int n_ctx = nt * 4;
   std::vector<WorkCtx> ctxs(n_ctx);
   std::mutex ctx_mu;
   std::vector<int> free_ctx;
@@ -139,7 +146,6 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, in
     const size_t usize = it.usize;
     size_t pos = i == 0 ? (size_t)skip0 : 0;
     it.have_stitched = false;
-    w.offs.clear();
     uint64_t ub_iv = 0;
     bool swallowed = false;  // the whole item is the middle of one huge record
     if (!carry.empty()) {
@@ -163,7 +169,12 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, in
     }
     if (swallowed) {
       carry.swap(w.stitched);
+      w.offs.clear();
+    } else if (it.guess_start == (int64_t)pos) {  // the worker's pre-walk started at the right byte: take it
+      ub_iv += it.guess_ub_iv;
+      carry.assign(buf + it.guess_tail, buf + usize);
     } else {
+      w.offs.clear();
       while (pos + 4 <= usize) {
         const uint32_t bs = rd_u32(buf + pos);
         if (bs < 32) throw Panic("Error reading BAM record: corrupt block_size");
@@ -225,6 +236,63 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, in
       if (h < n_items && items[h].inflated.load(std::memory_order_acquire)) continue;
       return;
     }
+  };
+
+  // A plausible BAM record header at buf[s..): sane block_size, reference ids, name length and NUL, field sizes.
+  auto plausible = [&](const uint8_t* buf, size_t s, size_t usize) {
+    if (s + 36 > usize) return false;
+    const uint32_t bs = rd_u32(buf + s);
+    if (bs < 32 || bs > (64u << 20)) return false;
+    const int32_t tid = (int32_t)rd_u32(buf + s + 4), pos = (int32_t)rd_u32(buf + s + 8), mtid = (int32_t)rd_u32(buf + s + 24);
+    if (tid < -1 || tid >= (int32_t)n_ref || mtid < -1 || mtid >= (int32_t)n_ref || pos < -1) return false;
+    const uint32_t l_name = buf[s + 12], n_cig = rd_u16(buf + s + 16), l_seq = rd_u32(buf + s + 20);
+    if (l_name == 0 || l_seq > (1u << 28)) return false;
+    const uint64_t fixed = 32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq;
+    if (fixed > bs) return false;
+    if (s + 36 + l_name <= usize && buf[s + 36 + l_name - 1] != 0) return false;
+    return true;
+  };
+  // Guess the first record boundary of an item and pre-walk its block_size chain while the data is cache-hot.
+  auto prewalk = [&](Item& it, WorkCtx& w, size_t index) {
+    const uint8_t* buf = w.buf.get();
+    const size_t usize = it.usize;
+    it.guess_start = -1;
+    w.offs.clear();
+    size_t start = (size_t)-1;
+    if (index == 0) {
+      start = (size_t)skip0;  // known exactly
+    } else {
+      const size_t limit = std::min<size_t>(usize, 1u << 18);
+      for (size_t s = 0; s < limit && start == (size_t)-1; ++s) {
+        if (!plausible(buf, s, usize)) continue;
+        size_t q = s;
+        int ok = 0;
+        while (ok < 6) {  // a run of six consistent headers (or reaching the end of the item) confirms the guess
+          if (q + 36 > usize) { ok = 6; break; }
+          if (!plausible(buf, q, usize)) break;
+          q += 4 + (size_t)rd_u32(buf + q);
+          ++ok;
+        }
+        if (ok >= 6) start = s;
+      }
+      if (start == (size_t)-1) return;  // nothing recognisable (e.g. the inside of one huge record): chain step walks it
+    }
+    size_t pos = start;
+    uint64_t ub = 0;
+    while (pos + 4 <= usize) {
+      const uint32_t bs = rd_u32(buf + pos);
+      if (bs < 32 || pos + 4 + (size_t)bs > usize) break;
+      w.offs.push_back((uint32_t)pos);
+      ub += rd_u16(buf + pos + 4 + 12);
+      pos += 4 + (size_t)bs;
+    }
+    if (pos + 4 <= usize && rd_u32(buf + pos) < 32) {  // corrupt chain: let the chain step raise the error
+      w.offs.clear();
+      return;
+    }
+    it.guess_start = (int64_t)start;
+    it.guess_tail = pos;
+    it.guess_ub_iv = ub;
   };
 
   auto extract = [&](size_t i, uint64_t& my_primaries) {
@@ -294,6 +362,7 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, in
             WorkCtx& w = ctxs[c];
             if (!w.buf) w.buf.reset(new uint8_t[max_item + 8]);
             bx.inflate(items[j].b0, items[j].b1, w.buf.get(), &zs);
+            prewalk(items[j], w, j);
             items[j].ctx = c;
             items[j].inflated.store(1, std::memory_order_release);
             t_inf += pipeline_now() - t0;

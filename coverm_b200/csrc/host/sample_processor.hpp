@@ -306,7 +306,7 @@ class DeviceSession {
       if (stream.is_raw()) bx.build(stream.raw_data(), stream.raw_size());
       else bx.build(p, n);
       const PipelineCounts pc = run_decode_pipeline(
-          bx, records_at, pool_.size(), batch_records_, batch_intervals_, n_staging_,
+          bx, records_at, n_ref, pool_.size(), batch_records_, batch_intervals_, n_staging_,
           [&](cmb_read_batch* b) {
             const double a = now_s();
             int r2 = cmb_acquire_batch(ctx_, b);
