@@ -331,6 +331,7 @@ inline CliResult run_cli(const std::vector<std::string>& args, const std::vector
       own = std::make_unique<DeviceSession>(o.device, o.threads);
       session = own.get();
     }
+    plan.printer.pool = &session->pool();
     DriverIO io{session, plan.params, &res.timings, &res.record_counts};
     if (o.sub == "contig") {
       res.reads_mapped = contig_coverage(inputs, taker, plan.estimators, !o.no_zeros, io);

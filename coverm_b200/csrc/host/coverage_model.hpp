@@ -27,6 +27,15 @@ inline std::string rust_display(F v) {  // Rust `{}` for f32/f64: shortest round
   return std::string(buf, r.ptr);
 }
 
+template <class F>
+inline void append_display(std::string& out, F v) {  // rust_display appended in place (no temporary string)
+  if (std::isnan(v)) { out += "NaN"; return; }
+  if (std::isinf(v)) { out += v < 0 ? "-inf" : "inf"; return; }
+  char buf[512];
+  auto r = std::to_chars(buf, buf + sizeof buf, v, std::chars_format::fixed);
+  out.append(buf, r.ptr);
+}
+
 struct ReadsMapped {  // lib.rs:53-57
   uint64_t num_mapped_reads = 0, num_reads = 0;
 };
@@ -95,12 +104,28 @@ class CoverageTaker {  // coverage_takers.rs:29-38 (trait) over the three Covera
   }
 
   // What CoverageTakerTypeIterator (coverage_takers.rs:265-377) yields: stoit by stoit, every entry index that any
-  // stoit recorded (ascending), zero-filled where this stoit has none.
-  std::vector<EntryAndCoverages> entries_by_stoit() const {
-    std::vector<EntryAndCoverages> v;
+  // stoit recorded (ascending), zero-filled where this stoit has none.  A Cell points at the first of the
+  // num_coverages values of (stoit, entry), or is null for "all zeros".
+  struct Cell {
+    size_t entry_index;
+    const Entry* first;
+    float at(size_t c) const { return first ? first[c].coverage : 0.0f; }
+  };
+  std::vector<std::vector<Cell>> cells_by_stoit() const {
     const size_t ns = stoit_names.size();
-    // union of entry indices in ascending order, via a k-way walk (each stoit's list is ascending in entry index)
-    for (size_t s = 0; s < ns; ++s) {
+    std::vector<std::vector<Cell>> out(ns);
+    if (ns == 1) {  // one sample: its own entries, in the order recorded (ascending entry index)
+      const auto& mine = coverages[0];
+      out[0].reserve(num_coverages ? mine.size() / num_coverages : 0);
+      std::optional<size_t> last;
+      for (size_t i = 0; i + num_coverages <= mine.size() && num_coverages; i += num_coverages) {
+        if (last && mine[i].entry_index <= *last) break;  // the reference's iterator stops at a non-ascending entry
+        out[0].push_back({mine[i].entry_index, &mine[i]});
+        last = mine[i].entry_index;
+      }
+      return out;
+    }
+    for (size_t s = 0; s < ns; ++s) {  // k-way walk over the stoits' lists (each ascending in entry index)
       std::vector<size_t> head(ns, 0);
       std::optional<size_t> last;
       for (;;) {
@@ -112,21 +137,27 @@ class CoverageTaker {  // coverage_takers.rs:29-38 (trait) over the three Covera
           if (!lowest || e < *lowest) lowest = e;
         }
         if (!lowest) break;
-        EntryAndCoverages ec;
-        ec.entry_index = *lowest;
-        ec.stoit_index = s;
         const auto& mine = coverages[s];
-        if (head[s] < mine.size() && mine[head[s]].entry_index == *lowest) {
-          for (size_t j = 0; j < num_coverages; ++j) ec.coverages.push_back(mine[head[s] + j].coverage);
-        } else {
-          ec.coverages.assign(num_coverages, 0.0f);
-        }
+        const bool have = head[s] < mine.size() && mine[head[s]].entry_index == *lowest;
+        out[s].push_back({*lowest, have ? &mine[head[s]] : nullptr});
         for (size_t k = 0; k < ns; ++k)
           if (head[k] < coverages[k].size() && coverages[k][head[k]].entry_index == *lowest) head[k] += num_coverages;
         last = *lowest;
-        v.push_back(std::move(ec));
       }
     }
+    return out;
+  }
+  std::vector<EntryAndCoverages> entries_by_stoit() const {
+    std::vector<EntryAndCoverages> v;
+    const auto cells = cells_by_stoit();
+    for (size_t s = 0; s < cells.size(); ++s)
+      for (const Cell& c : cells[s]) {
+        EntryAndCoverages ec;
+        ec.entry_index = c.entry_index;
+        ec.stoit_index = s;
+        for (size_t j = 0; j < num_coverages; ++j) ec.coverages.push_back(c.at(j));
+        v.push_back(std::move(ec));
+      }
     return v;
   }
 
@@ -408,6 +439,7 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
  public:
   enum class Kind { Streamed, SparseCached, DenseCached, MetabatAdjusted };
   Kind kind = Kind::Streamed;
+  ThreadPool* pool = nullptr;  // optional: rows are formatted in parallel blocks
 
   void print_headers(const std::string& entry_type, const std::vector<std::string>& headers, std::ostream& os) {  // :123-152
     if (kind == Kind::Streamed || kind == Kind::SparseCached) {
@@ -474,32 +506,47 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
     }
   }
 
+  // Formats rows [0, n) with row(i, std::string&) in parallel blocks and writes them in order.
+  template <class RowFn>
+  void write_rows(std::ostream& os, size_t n, RowFn row) {
+    constexpr size_t BLOCK = 4096;
+    const size_t n_blocks = (n + BLOCK - 1) / BLOCK;
+    std::vector<std::string> text(n_blocks);
+    auto do_block = [&](size_t b, int) {
+      std::string& t = text[b];
+      t.reserve(BLOCK * 48);
+      for (size_t i = b * BLOCK; i < std::min(n, (b + 1) * BLOCK); ++i) row(i, t);
+    };
+    if (pool && n_blocks > 1) pool->parallel_for(n_blocks, do_block);
+    else for (size_t b = 0; b < n_blocks; ++b) do_block(b, 0);
+    for (auto& t : text) os.write(t.data(), (std::streamsize)t.size());
+  }
+
   void sparse(const CoverageTaker& taker, std::ostream& os, const std::vector<ReadsMapped>& rm,
               const std::vector<size_t>& norm, std::optional<size_t> rpkm, std::optional<size_t> tpm) {  // :155-356
     const size_t nc = taker.num_coverages;
     size_t extra_cols = 0;
     for (auto& n : taker.entry_names)
       if (n) { extra_cols = tabs(*n); break; }
-    const auto all = taker.entries_by_stoit();
+    const auto cells = taker.cells_by_stoit();
     // The reference always emits the block of the first stoit (even when it is empty); later stoits only when they
     // have entries — which, by construction of the iterator, is whenever any stoit has entries.
-    size_t a = 0;
-    size_t stoit = 0;
-    for (;;) {
-      size_t b = a;
-      while (b < all.size() && all[b].stoit_index == stoit) ++b;
+    for (size_t stoit = 0; stoit < std::max<size_t>(1, cells.size()); ++stoit) {
       if (stoit >= taker.stoit_names.size()) throw Panic("index out of bounds");
+      if (stoit > 0 && cells[stoit].empty()) continue;
+      static const std::vector<CoverageTaker::Cell> none;
+      const auto& rows = cells.empty() ? none : cells[stoit];
       const std::string& name = taker.stoit_names[stoit];
       std::vector<float> totals(nc, 0.0f), mult(nc, 0.0f);
       for (size_t c : norm) {
         float t = 0.0f;
-        for (size_t i = a; i < b; ++i) t += all[i].coverages[c];  // sequential f32 sum in entry order (:220-224)
+        for (auto& r : rows) t += r.at(c);  // sequential f32 sum in entry order (:220-224)
         totals[c] = t;
         mult[c] = (float)rm[stoit].num_mapped_reads / (float)rm[stoit].num_reads;
       }
       if (tpm) {
         float t = 0.0f;
-        for (size_t i = a; i < b; ++i) t += all[i].coverages[*tpm];
+        for (auto& r : rows) t += r.at(*tpm);
         totals[*tpm] = t;
       }
       if (!norm.empty()) {
@@ -508,29 +555,25 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
         unmapped_columns(os, norm, nc, [&](size_t c) { return rust_display(100.0f * (1.0f - mult[c])); });
         os << '\n';
       }
-      for (size_t i = a; i < b; ++i) {
-        const auto& cov = all[i].coverages;
-        if (!taker.entry_names[all[i].entry_index]) throw ExitError(1, "Didn't find entry name string as expected");
-        os << name << '\t' << strip_cr(*taker.entry_names[all[i].entry_index]);
+      for (auto& r : rows)
+        if (!taker.entry_names[r.entry_index]) throw ExitError(1, "Didn't find entry name string as expected");
+      const uint64_t n_mapped = rm.empty() ? 0 : rm[stoit].num_mapped_reads;
+      write_rows(os, rows.size(), [&](size_t i, std::string& t) {
+        const auto& r = rows[i];
+        t += name;
+        t += '\t';
+        t += strip_cr(*taker.entry_names[r.entry_index]);
         for (size_t c = 0; c < nc; ++c) {
-          os << '\t';
-          if (in(norm, c)) {
-            os << rust_display(cov[c] * 100.0f * mult[c] / totals[c]);  // :285-286
-          } else if (rpkm && *rpkm == c) {
-            const uint64_t n = rm[stoit].num_mapped_reads;
-            os << rust_display(n == 0 ? 0.0f : cov[c] / (float)n);  // :300
-          } else if (tpm && *tpm == c) {
-            const uint64_t n = rm[stoit].num_mapped_reads;
-            os << rust_display(n == 0 ? 0.0 : (double)std::exp(std::log(cov[c]) - std::log(totals[c])) * 1000000.0);  // :320-323
-          } else {
-            os << rust_display(cov[c]);
-          }
+          t += '\t';
+          const float cov = r.at(c);
+          if (in(norm, c)) append_display(t, cov * 100.0f * mult[c] / totals[c]);  // :285-286
+          else if (rpkm && *rpkm == c) append_display(t, n_mapped == 0 ? 0.0f : cov / (float)n_mapped);  // :300
+          else if (tpm && *tpm == c)
+            append_display(t, n_mapped == 0 ? 0.0 : (double)std::exp(std::log(cov) - std::log(totals[c])) * 1000000.0);  // :320-323
+          else append_display(t, cov);
         }
-        os << '\n';
-      }
-      if (b >= all.size()) break;
-      a = b;
-      stoit = all[b].stoit_index;
+        t += '\n';
+      });
     }
   }
 
@@ -549,41 +592,41 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
       for (size_t s = 0; s < ns; ++s) unmapped_columns(os, norm, nc, [&](size_t) { return rust_display(100.0f * (1.0f - mult[s])); });
       os << '\n';
     }
-    std::vector<std::vector<EntryAndCoverages>> by_stoit;
+    const auto cells = taker.cells_by_stoit();
     std::vector<std::vector<float>> totals(ns, std::vector<float>(nc, 0.0f));
-    std::vector<std::vector<bool>> seeded(ns, std::vector<bool>(nc, false));
-    for (auto& ec : taker.entries_by_stoit()) {
+    for (size_t s = 0; s < cells.size(); ++s) {
       auto accumulate = [&](size_t c) {  // first value seeds the total, later ones are added (:457-477)
-        if (seeded[ec.stoit_index][c]) totals[ec.stoit_index][c] += ec.coverages[c];
-        else { totals[ec.stoit_index][c] = ec.coverages[c]; seeded[ec.stoit_index][c] = true; }
+        bool seeded = false;
+        float t = 0.0f;
+        for (auto& r : cells[s]) {
+          if (seeded) t += r.at(c);
+          else { t = r.at(c); seeded = true; }
+        }
+        totals[s][c] = t;
       };
       for (size_t c : norm) accumulate(c);
       if (tpm) accumulate(*tpm);
-      if (by_stoit.size() <= ec.stoit_index) by_stoit.emplace_back();
-      by_stoit[ec.stoit_index].push_back(ec);
     }
-    if (by_stoit.empty()) throw Panic("index out of bounds: the len is 0 but the index is 0");
-    for (size_t e = 0; e < by_stoit[0].size(); ++e) {
-      os << strip_cr(*taker.entry_names[by_stoit[0][e].entry_index]);
-      for (size_t s = 0; s < by_stoit.size(); ++s) {
-        const auto& cov = by_stoit[s][e].coverages;
-        for (size_t c = 0; c < cov.size(); ++c) {
-          os << '\t';
-          if (in(norm, c)) {
-            os << rust_display(cov[c] / totals[s][c] * 100.0f * mult[s]);  // :496-502
-          } else if (rpkm && *rpkm == c) {
-            const uint64_t n = rm[s].num_mapped_reads;
-            os << rust_display(n == 0 ? 0.0f : cov[c] / (float)n);  // :517
-          } else if (tpm && *tpm == c) {
-            const uint64_t n = rm[s].num_mapped_reads;
-            os << rust_display(n == 0 ? 0.0f : std::exp(std::log(cov[c]) - std::log(totals[s][c])) * 1000000.0f);  // :536-539
-          } else {
-            os << rust_display(cov[c]);
-          }
+    size_t n_filled = 0;  // the reference only materialises stoits that yielded entries
+    while (n_filled < cells.size() && !cells[n_filled].empty()) ++n_filled;
+    if (n_filled == 0) throw Panic("index out of bounds: the len is 0 but the index is 0");
+    write_rows(os, cells[0].size(), [&](size_t e, std::string& t) {
+      t += strip_cr(*taker.entry_names[cells[0][e].entry_index]);
+      for (size_t s = 0; s < n_filled; ++s) {
+        const auto& r = cells[s][e];
+        const uint64_t n_mapped = rm.empty() ? 0 : rm[s].num_mapped_reads;
+        for (size_t c = 0; c < nc; ++c) {
+          t += '\t';
+          const float cov = r.at(c);
+          if (in(norm, c)) append_display(t, cov / totals[s][c] * 100.0f * mult[s]);  // :496-502
+          else if (rpkm && *rpkm == c) append_display(t, n_mapped == 0 ? 0.0f : cov / (float)n_mapped);  // :517
+          else if (tpm && *tpm == c)
+            append_display(t, n_mapped == 0 ? 0.0f : std::exp(std::log(cov) - std::log(totals[s][c])) * 1000000.0f);  // :536-539
+          else append_display(t, cov);
         }
       }
-      os << '\n';
-    }
+      t += '\n';
+    });
   }
 };
 

@@ -31,17 +31,24 @@ inline double pipeline_now() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
 
+struct WorkCtx {  // pooled per-item scratch
+  std::unique_ptr<uint8_t[]> buf;
+  size_t cap = 0;
+  std::vector<uint32_t> offs;
+  std::vector<uint8_t> stitched;
+};
+// Scratch that outlives one sample: re-using the item buffers avoids re-faulting hundreds of MB of fresh pages from
+// 100+ threads at once on every sample.
+struct DecodeScratch {
+  std::vector<WorkCtx> ctxs;
+};
+
 // Runs the whole record stream (starting at uncompressed offset `records_at`) through the device context.
 // acquire()/submit() are the caller's wrappers around cmb_acquire_batch / cmb_submit_batch (called only from this thread).
 template <class Acquire, class Submit>
 PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, uint32_t n_ref, int n_threads, uint32_t cap_r,
-                                   uint32_t cap_i, uint32_t n_staging, Acquire acquire, Submit submit) {
+                                   uint32_t cap_i, uint32_t n_staging, DecodeScratch& scratch, Acquire acquire, Submit submit) {
   constexpr size_t ITEM_BYTES = 1u << 20;
-  struct WorkCtx {  // pooled per-item scratch
-    std::unique_ptr<uint8_t[]> buf;
-    std::vector<uint32_t> offs;
-    std::vector<uint8_t> stitched;
-  };
   struct Item {
     size_t b0 = 0, b1 = 0, usize = 0;
     std::atomic<int> inflated{0};
@@ -84,7 +91,8 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
 
   // ---- pooled contexts (bounds memory: 3 buffers per worker)
   const int n_ctx = nt * 4;
-  std::vector<WorkCtx> ctxs(n_ctx);
+  std::vector<WorkCtx>& ctxs = scratch.ctxs;
+  if ((int)ctxs.size() < n_ctx) ctxs.resize(n_ctx);
   std::mutex ctx_mu;
   std::vector<int> free_ctx;
   for (int k = 0; k < n_ctx; ++k) free_ctx.push_back(k);
@@ -360,7 +368,10 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
             }
             const double t0 = pipeline_now();
             WorkCtx& w = ctxs[c];
-            if (!w.buf) w.buf.reset(new uint8_t[max_item + 8]);
+            if (w.cap < max_item + 8) {
+              w.buf.reset(new uint8_t[max_item + 8]);
+              w.cap = max_item + 8;
+            }
             bx.inflate(items[j].b0, items[j].b1, w.buf.get(), &zs);
             prewalk(items[j], w, j);
             items[j].ctx = c;

@@ -130,6 +130,7 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
     uint64_t num_mapped_reads_total = 0;
     const uint32_t n = (uint32_t)r.header.names.size();
     std::vector<float> coverages(coverage_estimators.size());
+    const std::vector<uint64_t> contig_mode_unobserved{0};  // calculate_coverage(&[0]), contig.rs:65
     for (uint32_t tid = 0; tid < n; ++tid) {
       if (r.rows[tid].n_records == 0) {  // never seen: print_previous_zero_coverage_contigs (:255-277)
         if (print_zero_coverage_contigs) {
@@ -143,7 +144,7 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
       bool has_nonzero = false;
       for (size_t k = 0; k < coverage_estimators.size(); ++k) {
         coverage_estimators[k].add_contig(ob);
-        coverages[k] = coverage_estimators[k].calculate_coverage({0});
+        coverages[k] = coverage_estimators[k].calculate_coverage(contig_mode_unobserved);
         has_nonzero = has_nonzero || coverages[k] > 0.0f;
       }
       if (has_nonzero) num_mapped_reads_total += ob.num_mapped_reads;

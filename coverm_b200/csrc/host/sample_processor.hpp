@@ -306,7 +306,7 @@ class DeviceSession {
       if (stream.is_raw()) bx.build(stream.raw_data(), stream.raw_size());
       else bx.build(p, n);
       const PipelineCounts pc = run_decode_pipeline(
-          bx, records_at, n_ref, pool_.size(), batch_records_, batch_intervals_, n_staging_,
+          bx, records_at, n_ref, pool_.size(), batch_records_, batch_intervals_, n_staging_, scratch_,
           [&](cmb_read_batch* b) {
             const double a = now_s();
             int r2 = cmb_acquire_batch(ctx_, b);
@@ -419,6 +419,7 @@ class DeviceSession {
 
  private:
   ThreadPool pool_;
+  DecodeScratch scratch_;
   cmb_ctx* ctx_ = nullptr;
   uint32_t batch_records_ = 0, batch_intervals_ = 0, n_staging_ = 0;
   uint32_t shard_begin_ = 0, shard_end_ = 0xffffffffu;
