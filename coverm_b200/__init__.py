@@ -121,15 +121,17 @@ def extract_tuples(path, threads=None):
 _lib = None
 
 
-def load_library():
-    """Load libcoverm_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if it is missing."""
+def load_library(path=None):
+    """Load libcoverm_b200.so (built in-tree by __graft_entry__.build()).  Fails loudly if it is missing.
+    `path` is for tests that bind another build of the same ABI explicitly; the product always uses LIB_PATH."""
     global _lib
-    if _lib is not None:
+    if path is None and _lib is not None:
         return _lib
-    if not os.path.exists(LIB_PATH):
-        raise CmbError(f"{LIB_PATH} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+    lib_path = path or LIB_PATH
+    if not os.path.exists(lib_path):
+        raise CmbError(f"{lib_path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
                        "(there is no Python/CPU fallback)")
-    lib = C.CDLL(LIB_PATH)
+    lib = C.CDLL(lib_path)
     lib.cmb_abi_version.restype = C.c_int
     lib.cmb_create.argtypes = [C.POINTER(DeviceCfg), C.POINTER(C.c_void_p)]
     lib.cmb_destroy.argtypes = [C.c_void_p]
@@ -160,7 +162,8 @@ def load_library():
     lib.cmbh_extract_tuples.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Tuples)]
     lib.cmbh_free_tuples.argtypes = [C.POINTER(Tuples)]
     lib.cmbh_free_tuples.restype = None
-    _lib = lib
+    if path is None:
+        _lib = lib
     return lib
 
 
@@ -172,8 +175,8 @@ class RunResult:
 class Session:
     """One GPU context + host thread pool (cmbh_session): ``run(argv)`` is `coverm <argv...>` in-process."""
 
-    def __init__(self, device=0, threads=None):
-        lib = load_library()
+    def __init__(self, device=0, threads=None, lib=None):
+        lib = lib or load_library()
         self._lib = lib
         self._h = C.c_void_p()
         threads = threads or (os.cpu_count() or 1)
