@@ -36,6 +36,23 @@ def log(*a):
     print("[bench]", *a, file=sys.stderr, flush=True)
 
 
+def effective_cpus():
+    """CPUs this process may actually use: the smaller of the visible CPUs and the cgroup CPU quota
+    (the GPU boxes expose 128 logical CPUs but cap the container at 24 via cpu.max; more threads only get throttled)."""
+    n = os.cpu_count() or 1
+    try:
+        n = min(n, len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
+    try:
+        quota, period = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if quota != "max":
+            n = min(n, max(1, int(int(quota) / int(period))))
+    except Exception:
+        pass
+    return n
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
@@ -141,8 +158,17 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    ncpu = os.cpu_count() or 1
+    ncpu = effective_cpus()
     threads = max(1, ncpu // world)
+    # stdout carries exactly one JSON line: everything else (NCCL banners, library chatter) goes to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
+
+    def emit(line):
+        sys.stdout.flush()
+        os.dup2(real_stdout, 1)
+        print(json.dumps(line), flush=True)
+        os.dup2(2, 1)
     os.makedirs(args.workdir, exist_ok=True)
 
     if args.impl == "reference":
@@ -156,7 +182,7 @@ def main():
                            "contigs": args.contigs // args.cpu_fraction, "reads": args.reads // args.cpu_fraction},
                 "cpu_baseline": cpu,
                 "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
-        print(json.dumps(line), flush=True)
+        emit(line)
         return
 
     import numpy as np
@@ -316,7 +342,7 @@ def main():
                        "contigs": args.contigs, "reads_per_gpu": n_rec, "bases_per_gpu": int(info["bases"]),
                        "parallelism": f"{world} sample(s), one per GPU" + ("; NCCL all-gather of the per-contig table" if world > 1 else ""),
                        "l2": f"inputs larger than L2: {algo_bytes / 1e9:.1f} GB delta arena + {(39 * n_rec + 8 * n_iv) / 1e6:.0f} MB tuples per step",
-                       "host_threads_per_rank": threads},
+                       "host_threads_per_rank": threads, "host_cpus_effective": ncpu, "host_cpus_visible": os.cpu_count()},
             "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "seconds_per_step": e2e_s,
@@ -331,7 +357,7 @@ def main():
                                     "k3_finalize": mean(k3_ms), "stream_total": mean(dev_ms), "wall_per_step": wall_ms / args.steps},
             "cpu_baseline": cpu, "parity_vs_oracle_on_cpu_sample": parity,
         }
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
