@@ -13,8 +13,11 @@
 #include <unistd.h>
 #include <zlib.h>
 
+#include "fast_inflate.hpp"
+
 #include <cstring>
 #include <map>
+#include <memory>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -27,6 +30,39 @@ namespace cmbh {
 
 struct Panic : std::runtime_error {  // the reference would panic!() here (exit status 101)
   using std::runtime_error::runtime_error;
+};
+
+// One BGZF block -> its uncompressed bytes: the fast decoder first, checked against the block footer's CRC32; zlib's
+// inflate() when the fast decoder declines or the checksum disagrees (htslib verifies the same CRC in bgzf.c).
+class BgzfInflater {
+ public:
+  BgzfInflater() : fast_(new FastInflate) {
+    memset(&zs_, 0, sizeof zs_);
+    if (inflateInit2(&zs_, -15) != Z_OK) throw Panic("zlib init failed");
+  }
+  ~BgzfInflater() { inflateEnd(&zs_); }
+  BgzfInflater(const BgzfInflater&) = delete;
+  BgzfInflater& operator=(const BgzfInflater&) = delete;
+  // cdata[clen .. clen+8) is the footer (CRC32, ISIZE).  Returns false on a corrupt block.
+  bool block(const uint8_t* cdata, size_t clen, uint8_t* out, uint32_t isize) {
+    if (isize == 0) return true;
+    uint32_t want;
+    memcpy(&want, cdata + clen, 4);
+    if (fast_->run(cdata, clen, out, isize) && (uint32_t)crc32(0, out, isize) == want) return true;
+    ++slow_blocks;
+    inflateReset(&zs_);
+    zs_.next_in = const_cast<Bytef*>(cdata);
+    zs_.avail_in = (uInt)clen;
+    zs_.next_out = out;
+    zs_.avail_out = isize;
+    if (inflate(&zs_, Z_FINISH) != Z_STREAM_END || zs_.avail_out != 0) return false;
+    return (uint32_t)crc32(0, out, isize) == want;
+  }
+  uint64_t slow_blocks = 0;
+
+ private:
+  std::unique_ptr<FastInflate> fast_;
+  z_stream zs_;
 };
 struct ExitError : std::runtime_error {  // error!(..); process::exit(code)
   int code;
@@ -138,23 +174,11 @@ class InflateStream {
     const size_t per = 4;
     const size_t n_tasks = (blocks_.size() + per - 1) / per;
     pool_.parallel_for(n_tasks, [&](size_t task, int) {
-      z_stream zs;
-      memset(&zs, 0, sizeof zs);
-      if (inflateInit2(&zs, -15) != Z_OK) {
-        bad = true;
-        return;
-      }
+      BgzfInflater inf;
       for (size_t i = task * per; i < std::min(blocks_.size(), (task + 1) * per); ++i) {
         const Block& b = blocks_[i];
-        if (b.isize == 0) continue;
-        inflateReset(&zs);
-        zs.next_in = const_cast<Bytef*>(p_ + b.cdata);
-        zs.avail_in = (uInt)b.clen;
-        zs.next_out = out + b.out_off;
-        zs.avail_out = b.isize;
-        if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.avail_out != 0) bad = true;
+        if (!inf.block(p_ + b.cdata, b.clen, out + b.out_off, b.isize)) bad = true;
       }
-      inflateEnd(&zs);
     });
     if (bad) throw Panic("Error reading BAM record: BGZF inflate failed");
     return true;

@@ -75,7 +75,7 @@ class BlockIndex {
   }
 
   // Inflate blocks [b0, b1) into dst (which has room for ustart[b1]-ustart[b0] bytes).
-  void inflate(size_t b0, size_t b1, uint8_t* dst, z_stream* zs) const {
+  void inflate(size_t b0, size_t b1, uint8_t* dst, BgzfInflater& inf) const {
     for (size_t b = b0; b < b1; ++b) {
       const BlockRef& r = blocks[b];
       uint8_t* out = dst + (ustart[b] - ustart[b0]);
@@ -83,13 +83,7 @@ class BlockIndex {
         memcpy(out, p + r.cdata, r.clen);
         continue;
       }
-      if (r.isize == 0) continue;
-      inflateReset(zs);
-      zs->next_in = const_cast<Bytef*>(p + r.cdata);
-      zs->avail_in = (uInt)r.clen;
-      zs->next_out = out;
-      zs->avail_out = r.isize;
-      if (::inflate(zs, Z_FINISH) != Z_STREAM_END || zs->avail_out != 0) throw Panic("Error reading BAM record: BGZF inflate failed");
+      if (!inf.block(p + r.cdata, r.clen, out, r.isize)) throw Panic("Error reading BAM record: BGZF inflate failed");
     }
   }
 };

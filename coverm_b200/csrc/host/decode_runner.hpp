@@ -331,9 +331,7 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
     double t_inf = 0, t_scan = 0, t_ext = 0, t_idle = 0;
     uint64_t my_records = 0, my_primaries = 0;
     try {
-      z_stream zs;
-      memset(&zs, 0, sizeof zs);
-      if (inflateInit2(&zs, -15) != Z_OK) throw Panic("zlib init failed");
+      BgzfInflater inflater;
       bool inflate_done = false;
       while (!abort) {
         // 1. extraction first: it frees buffers and completes batches
@@ -372,7 +370,7 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
               w.buf.reset(new uint8_t[max_item + 8]);
               w.cap = max_item + 8;
             }
-            bx.inflate(items[j].b0, items[j].b1, w.buf.get(), &zs);
+            bx.inflate(items[j].b0, items[j].b1, w.buf.get(), inflater);
             prewalk(items[j], w, j);
             items[j].ctx = c;
             items[j].inflated.store(1, std::memory_order_release);
@@ -388,7 +386,6 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
         std::this_thread::sleep_for(std::chrono::microseconds(20));
         t_idle += pipeline_now() - t0;
       }
-      inflateEnd(&zs);
     } catch (...) {
       fail(std::current_exception());
     }

@@ -33,11 +33,9 @@ class FastInflate {
         const uint32_t len = (uint32_t)bitbuf_ & 0xffff, nlen = ((uint32_t)bitbuf_ >> 16) & 0xffff;
         consume(32);
         if ((len ^ nlen) != 0xffff) return false;
-        // give the whole bytes still in the bit buffer back to the input
-        ip_ -= bitcnt_ >> 3;
-        bitbuf_ = 0;
-        bitcnt_ = 0;
-        if (overrun_ || (size_t)(in_end_ - ip_) < len || (size_t)(out_end - op) < len) return false;
+        // give the whole (real) bytes still in the bit buffer back to the input
+        if (!unload()) return false;
+        if ((size_t)(in_end_ - ip_) < len || (size_t)(out_end - op) < len) return false;
         memcpy(op, ip_, len);
         op += len;
         ip_ += len;
@@ -53,7 +51,7 @@ class FastInflate {
       }
       if (bfinal) break;
     }
-    return op == out_end && !overrun_;
+    return op == out_end && bitcnt_ >= overrun_ * 8;
   }
 
  private:
@@ -82,6 +80,16 @@ class FastInflate {
   void consume(int n) {
     bitbuf_ >>= n;
     bitcnt_ -= n;
+  }
+  // Return the unread whole bytes to the input; false if bits past the end of the input have been consumed.
+  bool unload() {
+    const int held = bitcnt_ >> 3;
+    if (overrun_ > held) return false;
+    ip_ -= held - overrun_;
+    overrun_ = 0;
+    bitcnt_ &= 7;
+    bitbuf_ &= (1ull << bitcnt_) - 1;
+    return true;
   }
   void refill_safe() {
     while (bitcnt_ <= 56) {
@@ -247,7 +255,7 @@ class FastInflate {
         while (rep--) lens[n++] = (uint8_t)val;
       }
     }
-    if (overrun_) return false;
+    if (bitcnt_ < overrun_ * 8) return false;
     if (lens[256] == 0) return false;  // no end-of-block code
     if (!build_table(lens, hlit, LITLEN_BITS, litlen_, (int)(sizeof litlen_ / 4), litlen_payload)) return false;
     if (!build_table(lens + hlit, hdist, DIST_BITS, dist_, (int)(sizeof dist_ / 4), dist_payload)) return false;
@@ -261,11 +269,13 @@ class FastInflate {
     uint64_t bitbuf = bitbuf_;
     int bitcnt = bitcnt_;
     const uint8_t* ip = ip_;
-    const uint8_t* const in_fast_end = in_end_;  // 8 readable bytes follow in_end_ (caller's contract)
+    // two 8-byte loads per iteration, the second up to 7 bytes further on: stay 8 bytes clear of the end so that both
+    // remain inside the 8 readable bytes the caller guarantees after in_end_
+    const uint8_t* const in_fast_end = in_end_ - ip_ >= 8 ? in_end_ - 8 : ip_ - 1;
     constexpr uint32_t LMASK = (1u << LITLEN_BITS) - 1, DMASK = (1u << DIST_BITS) - 1;
     bool ok = true, done = false;
     // ---- fast loop: far from both ends, no per-symbol bounds checks
-    while (ip < in_fast_end && out_end - op > 320) {
+    while (ip <= in_fast_end && out_end - op > 320) {
       bitbuf |= load64(ip) << bitcnt;
       ip += (63 - bitcnt) >> 3;
       bitcnt |= 56;
@@ -343,17 +353,11 @@ class FastInflate {
       }
     }
     // hand the bit reader back (whole unread bytes return to the input so that the safe loop can bound-check)
-    ip -= bitcnt >> 3;
-    bitbuf &= (1ull << (bitcnt & 7)) - 1;
-    bitcnt &= 7;
-    if (ip > in_end_) {  // the fast loop's last refill reached into the footer
-      const int back = (int)(ip - in_end_);
-      overrun_ += back;
-      ip = in_end_;
-    }
     ip_ = ip;
     bitbuf_ = bitbuf;
     bitcnt_ = bitcnt;
+    if (!unload()) return false;
+    if (ip_ > in_end_) return false;  // bits of the footer were consumed as stream bits
     if (!ok) return false;
     if (done) {
       op_ref = op;
@@ -397,7 +401,7 @@ class FastInflate {
       for (uint32_t k = 0; k < len; ++k) op[k] = src[k];
       op += len;
     }
-    if (overrun_ > 8) return false;  // consumed real bits that were never there
+    if (bitcnt_ < overrun_ * 8) return false;  // consumed bits that were never there
     op_ref = op;
     return true;
   }
