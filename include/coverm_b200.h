@@ -101,7 +101,7 @@ typedef struct cmb_filter_mode {
  * valid from cmb_acquire_batch until the matching cmb_submit_batch (several batches may
  * be acquired at once, up to n_staging; cmb_submit_batch submits the oldest one).
  * Record i covers intervals [iv_begin[i], iv_begin[i+1]) — the host writes
- * iv_begin[n_records] = n_intervals.  39 B per record + 8 B per interval.
+ * iv_begin[n_records] = n_intervals.  40 B per record + 8 B per interval.
  * An interval whose iv_start is CMB_IV_PAD is an unused pool slot and is ignored (lets
  * parallel decoders reserve interval space by an upper bound). */
 #define CMB_IV_PAD INT32_MIN
