@@ -87,7 +87,7 @@ class HostResult(C.Structure):
 
 DEVICE_SYMBOLS = ["cmb_abi_version", "cmb_create", "cmb_destroy", "cmb_last_error", "cmb_set_reference",
                   "cmb_set_params", "cmb_begin_sample", "cmb_acquire_batch", "cmb_submit_batch",
-                  "cmb_submit_device_batch", "cmb_end_sample", "cmb_fetch_pairs", "cmb_end_sample_device",
+                  "cmb_submit_device_batch", "cmb_submit_bgzf", "cmb_end_sample", "cmb_fetch_pairs", "cmb_end_sample_device",
                   "cmb_get_timing", "cmb_stream"]
 class Tuples(C.Structure):
     _fields_ = [("n_contigs", C.c_uint32), ("contig_len", C.POINTER(C.c_uint64)), ("n_records", C.c_uint64),

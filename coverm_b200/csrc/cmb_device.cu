@@ -32,8 +32,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <atomic>
 #include <string>
+#include <thread>
 #include <vector>
+
+#include <zlib.h>
 
 #include "../../include/coverm_b200.h"
 
@@ -43,6 +47,7 @@ namespace {
 #include "cmb_k1b.cuh"
 #include "cmb_k2.cuh"
 #include "cmb_k3.cuh"
+#include "cmb_decode.cuh"
 
 // ------------------------------------------------------------------------------------------------ host context
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -105,6 +110,28 @@ struct cmb_ctx {
   std::vector<std::pair<cudaEvent_t, cudaEvent_t>> k1_events;
   uint32_t k1_events_used = 0;
   uint64_t n_records = 0, n_intervals = 0;
+  // device-side decode (cmb_submit_bgzf); every buffer is grow-only and reused across samples
+  struct Decode {
+    uint8_t* d_comp = nullptr;
+    size_t comp_cap = 0;
+    uint8_t* d_inflated = nullptr;
+    size_t infl_cap = 0;
+    uint64_t *d_coff = nullptr, *d_ustart = nullptr, *d_guess = nullptr, *d_exit = nullptr, *d_rec_base = nullptr, *d_cig_base = nullptr;
+    uint32_t *d_clen = nullptr, *d_isize = nullptr, *d_status = nullptr, *d_nrec = nullptr, *d_ncig = nullptr, *d_dirty = nullptr;
+    size_t blocks_cap = 0;
+    uint32_t* d_tickets = nullptr;
+    size_t tickets_cap = 0;
+    uint32_t* d_cnt = nullptr;  // [0] inflate failures [1] decode error bits [2] chain changed [4..5] n_primary [6..9] totals
+    uint64_t* d_rec_off = nullptr;
+    size_t rec_cap = 0;
+    void* d_tuple_slab = nullptr;
+    size_t tuple_slab_bytes = 0;
+    std::vector<void*> pinned;
+    std::vector<cudaStream_t> streams;
+    std::vector<cudaEvent_t> slot_events, done_events;
+    cudaEvent_t ev[6]{};
+    bool have_events = false;
+  } dec;
 };
 
 namespace {
@@ -433,6 +460,18 @@ void cmb_destroy(cmb_ctx* c) {
     if (e) cudaEventDestroy(e);
   cudaFree(c->d_counters);
   cudaFree(c->d_block_minmax);
+  {
+    auto& d = c->dec;
+    cudaFree(d.d_comp); cudaFree(d.d_inflated); cudaFree(d.d_coff); cudaFree(d.d_ustart); cudaFree(d.d_guess); cudaFree(d.d_exit);
+    cudaFree(d.d_rec_base); cudaFree(d.d_cig_base); cudaFree(d.d_clen); cudaFree(d.d_isize); cudaFree(d.d_status); cudaFree(d.d_nrec);
+    cudaFree(d.d_ncig); cudaFree(d.d_dirty); cudaFree(d.d_tickets); cudaFree(d.d_cnt); cudaFree(d.d_rec_off); cudaFree(d.d_tuple_slab);
+    for (auto p : d.pinned) cudaFreeHost(p);
+    for (auto st : d.streams) cudaStreamDestroy(st);
+    for (auto e : d.slot_events) cudaEventDestroy(e);
+    for (auto e : d.done_events) cudaEventDestroy(e);
+    if (d.have_events)
+      for (auto e : d.ev) cudaEventDestroy(e);
+  }
   if (c->stream) cudaStreamDestroy(c->stream);
   delete c;
 }
@@ -680,3 +719,331 @@ int cmb_get_timing(const cmb_ctx* c, cmb_sample_timing* out) {
 void* cmb_stream(cmb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
 }  // extern "C"
+
+// ------------------------------------------------------------------------------------------------ device-side decode
+namespace {
+constexpr size_t DEC_COPY_CHUNK = 8u << 20;    // pinned staging slot
+constexpr size_t DEC_WINDOW_BYTES = 32u << 20; // compressed bytes per copy+inflate window
+constexpr size_t DEC_SLACK = 1024;
+
+template <class T>
+int dec_grow(cmb_ctx* c, T*& p, size_t& cap, size_t need, size_t extra_bytes = 0) {
+  if (cap >= need && p) return CMB_OK;
+  cudaFree(p);
+  p = nullptr;
+  cap = 0;
+  const size_t want = need + need / 8 + 16;
+  CU_TRY(c, cudaMalloc(&p, want * sizeof(T) + extra_bytes));
+  cap = want;
+  return CMB_OK;
+}
+}  // namespace
+
+extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) {
+  if (!c || !in || !out || !in->data || !in->block_coffset || !in->block_clen || !in->block_isize)
+    return fail(c, CMB_E_ARG, "cmb_submit_bgzf: null argument");
+  if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: no sample in progress");
+  if (c->n_acquired) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: a staging batch is still acquired");
+  if (c->mode.filter_pairs) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: pair filtering needs host mate matching");
+  *out = cmb_bgzf_result{};
+  const uint32_t nb = in->n_blocks;
+  if (nb == 0) return CMB_OK;
+  CU_TRY(c, cudaSetDevice(c->device));
+  auto& d = c->dec;
+  // ---- host block table
+  std::vector<uint64_t> ustart((size_t)nb + 1, 0);
+  for (uint32_t b = 0; b < nb; ++b) {
+    if (in->block_coffset[b] + in->block_clen[b] + 8 > in->size) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: block %u lies outside the data", b);
+    ustart[b + 1] = ustart[b] + in->block_isize[b];
+  }
+  const uint64_t total = ustart[nb];
+  if (in->records_at > total) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: records_at beyond the end of the stream");
+  if (in->records_at == total) return CMB_OK;  // header only
+  uint32_t first_block = (uint32_t)(std::upper_bound(ustart.begin(), ustart.end(), in->records_at) - ustart.begin()) - 1;
+  // ---- buffers
+  size_t dummy_cap;
+  int rc;
+  if ((rc = dec_grow(c, d.d_comp, d.comp_cap, (size_t)in->size + DEC_SLACK))) return rc;
+  if ((rc = dec_grow(c, d.d_inflated, d.infl_cap, (size_t)total + DEC_SLACK))) return rc;
+  if (d.blocks_cap < (size_t)nb + 1 || !d.d_coff) {
+    const size_t want = (size_t)nb + nb / 8 + 64;
+    cudaFree(d.d_coff); cudaFree(d.d_ustart); cudaFree(d.d_guess); cudaFree(d.d_exit); cudaFree(d.d_rec_base); cudaFree(d.d_cig_base);
+    cudaFree(d.d_clen); cudaFree(d.d_isize); cudaFree(d.d_status); cudaFree(d.d_nrec); cudaFree(d.d_ncig); cudaFree(d.d_dirty);
+    d.d_coff = d.d_ustart = d.d_guess = d.d_exit = d.d_rec_base = d.d_cig_base = nullptr;
+    d.d_clen = d.d_isize = d.d_status = d.d_nrec = d.d_ncig = d.d_dirty = nullptr;
+    d.blocks_cap = 0;
+    CU_TRY(c, cudaMalloc(&d.d_coff, 8 * want)); CU_TRY(c, cudaMalloc(&d.d_ustart, 8 * want)); CU_TRY(c, cudaMalloc(&d.d_guess, 8 * want));
+    CU_TRY(c, cudaMalloc(&d.d_exit, 8 * want)); CU_TRY(c, cudaMalloc(&d.d_rec_base, 8 * want)); CU_TRY(c, cudaMalloc(&d.d_cig_base, 8 * want));
+    CU_TRY(c, cudaMalloc(&d.d_clen, 4 * want)); CU_TRY(c, cudaMalloc(&d.d_isize, 4 * want)); CU_TRY(c, cudaMalloc(&d.d_status, 4 * want));
+    CU_TRY(c, cudaMalloc(&d.d_nrec, 4 * want)); CU_TRY(c, cudaMalloc(&d.d_ncig, 4 * want)); CU_TRY(c, cudaMalloc(&d.d_dirty, 4 * want));
+    d.blocks_cap = want;
+  }
+  if (!d.d_cnt) CU_TRY(c, cudaMalloc(&d.d_cnt, 64));
+  if (!d.have_events) {
+    for (auto& e : d.ev) CU_TRY(c, cudaEventCreate(&e));
+    d.have_events = true;
+  }
+  (void)dummy_cap;
+  // ---- windows of whole blocks, ~DEC_WINDOW_BYTES of file each
+  struct Window { uint32_t b0, b1; uint64_t byte0, byte1; };
+  std::vector<Window> windows;
+  {
+    uint32_t b = 0;
+    uint64_t byte0 = 0;
+    while (b < nb) {
+      uint32_t e = b;
+      uint64_t byte1 = byte0;
+      while (e < nb && (e == b || in->block_coffset[e] + in->block_clen[e] + 8 - byte0 <= DEC_WINDOW_BYTES)) {
+        byte1 = in->block_coffset[e] + in->block_clen[e] + 8;
+        ++e;
+      }
+      if (e == nb) byte1 = in->size;
+      windows.push_back({b, e, byte0, byte1});
+      b = e;
+      byte0 = byte1;
+    }
+  }
+  if (d.tickets_cap < windows.size() || !d.d_tickets) {
+    cudaFree(d.d_tickets);
+    d.d_tickets = nullptr;
+    d.tickets_cap = 0;
+    const size_t want = windows.size() * 2 + 64;
+    CU_TRY(c, cudaMalloc(&d.d_tickets, 4 * want));
+    d.tickets_cap = want;
+  }
+  // ---- copy threads, their streams and pinned slots
+  cudaPointerAttributes attr{};
+  const bool src_pinned = cudaPointerGetAttributes(&attr, in->data) == cudaSuccess && attr.type == cudaMemoryTypeHost;
+  cudaGetLastError();  // cudaPointerGetAttributes on pageable memory may leave a sticky-free error code
+  uint32_t T = in->copy_threads ? in->copy_threads : 4;
+  T = std::min<uint32_t>(std::min<uint32_t>(T, 16), (uint32_t)windows.size());
+  if (src_pinned) T = std::min<uint32_t>(T, 2);
+  while (d.streams.size() < T) {
+    cudaStream_t st;
+    CU_TRY(c, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+    d.streams.push_back(st);
+    cudaEvent_t e;
+    CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    d.done_events.push_back(e);
+    for (int k = 0; k < 2; ++k) {
+      CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      d.slot_events.push_back(e);
+      void* p = nullptr;
+      CU_TRY(c, cudaHostAlloc(&p, DEC_COPY_CHUNK, cudaHostAllocDefault));
+      d.pinned.push_back(p);
+    }
+  }
+  // ---- upload the block table, reset counters (ctx stream), then let the copy streams start after it
+  CU_TRY(c, cudaEventRecord(d.ev[0], c->stream));
+  CU_TRY(c, cudaMemcpyAsync(d.d_coff, in->block_coffset, 8ull * nb, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(d.d_clen, in->block_clen, 4ull * nb, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(d.d_isize, in->block_isize, 4ull * nb, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(d.d_ustart, ustart.data(), 8ull * (nb + 1), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.d_cnt, 0, 64, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * windows.size(), c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.d_inflated + total, 0, DEC_SLACK, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.d_comp + in->size, 0, DEC_SLACK, c->stream));
+  CU_TRY(c, cudaEventRecord(d.ev[1], c->stream));
+  CU_TRY(c, cudaFuncSetAttribute(kd_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
+  for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(d.streams[t], d.ev[1], 0));
+  std::atomic<size_t> next_window{0};
+  std::atomic<int> first_err{0};
+  auto worker = [&](uint32_t t) {
+    cudaSetDevice(c->device);
+    cudaStream_t st = d.streams[t];
+    int slot = 0;
+    bool used[2] = {false, false};
+    auto check = [&](cudaError_t e) {
+      if (e != cudaSuccess) {
+        int z = 0;
+        first_err.compare_exchange_strong(z, (int)e);
+      }
+      return e == cudaSuccess;
+    };
+    for (;;) {
+      const size_t w = next_window.fetch_add(1);
+      if (w >= windows.size() || first_err.load()) break;
+      const Window& win = windows[w];
+      if (src_pinned) {
+        if (!check(cudaMemcpyAsync(d.d_comp + win.byte0, in->data + win.byte0, win.byte1 - win.byte0, cudaMemcpyHostToDevice, st))) break;
+      } else {
+        for (uint64_t o = win.byte0; o < win.byte1; o += DEC_COPY_CHUNK) {
+          const size_t n = (size_t)std::min<uint64_t>(DEC_COPY_CHUNK, win.byte1 - o);
+          const size_t si = (size_t)t * 2 + slot;
+          if (used[slot] && !check(cudaEventSynchronize(d.slot_events[si]))) return;
+          memcpy(d.pinned[si], in->data + o, n);
+          if (!check(cudaMemcpyAsync(d.d_comp + o, d.pinned[si], n, cudaMemcpyHostToDevice, st))) return;
+          if (!check(cudaEventRecord(d.slot_events[si], st))) return;
+          used[slot] = true;
+          slot ^= 1;
+        }
+      }
+      InflateArgs a{};
+      a.comp = d.d_comp; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
+      a.b0 = win.b0; a.b1 = win.b1; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets + w; a.fail_count = d.d_cnt + 0;
+      const uint32_t warps = win.b1 - win.b0;
+      const uint32_t grid = std::min<uint32_t>((warps + INF_WARPS - 1) / INF_WARPS, (uint32_t)c->sm_count * 2);
+      kd_inflate<<<grid, INF_WARPS * 32, INF_SMEM_BYTES, st>>>(a);
+      if (!check(cudaGetLastError())) break;
+    }
+    check(cudaEventRecord(d.done_events[t], st));
+  };
+  {
+    std::vector<std::thread> threads;
+    for (uint32_t t = 1; t < T; ++t) threads.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : threads) th.join();
+  }
+  if (first_err.load()) return fail(c, CMB_E_CUDA, "cmb_submit_bgzf: copy/inflate stage failed: %s", cudaGetErrorString((cudaError_t)first_err.load()));
+  for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(c->stream, d.done_events[t], 0));
+  CU_TRY(c, cudaEventRecord(d.ev[2], c->stream));
+  // ---- blocks the device declined: zlib on the host, patched into the inflated stream
+  uint32_t h_cnt[16];
+  CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (h_cnt[0]) {
+    std::vector<uint32_t> status(nb);
+    CU_TRY(c, cudaMemcpy(status.data(), d.d_status, 4ull * nb, cudaMemcpyDeviceToHost));
+    if (getenv("CMB_DECODE_VERIFY")) {
+      uint32_t hist[32] = {0};
+      for (uint32_t b = 0; b < nb; ++b) hist[std::min<uint32_t>(status[b], 31)]++;
+      fprintf(stderr, "#decode_status");
+      for (int k = 0; k < 32; ++k)
+        if (hist[k]) fprintf(stderr, "\t%d:%u", k, hist[k]);
+      fprintf(stderr, "\n");
+    }
+    std::vector<uint8_t> tmp(65536 + 64);
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return fail(c, CMB_E_NOMEM, "zlib init failed");
+    for (uint32_t b = 0; b < nb; ++b) {
+      if (status[b] == INF_OK) continue;
+      const uint32_t isz = in->block_isize[b];
+      if (tmp.size() < isz) tmp.resize(isz);
+      inflateReset(&zs);
+      zs.next_in = const_cast<Bytef*>(in->data + in->block_coffset[b]);
+      zs.avail_in = in->block_clen[b];
+      zs.next_out = tmp.data();
+      zs.avail_out = isz;
+      uint32_t want_crc;
+      memcpy(&want_crc, in->data + in->block_coffset[b] + in->block_clen[b], 4);
+      if (inflate(&zs, Z_FINISH) != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(0, tmp.data(), isz) != want_crc) {
+        inflateEnd(&zs);
+        return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: BGZF block %u does not inflate", b);
+      }
+      CU_TRY(c, cudaMemcpy(d.d_inflated + ustart[b], tmp.data(), isz, cudaMemcpyHostToDevice));
+      out->n_blocks_host += 1;
+    }
+    inflateEnd(&zs);
+  }
+  if (getenv("CMB_DECODE_VERIFY")) {  // debugging aid: compare every device-inflated block with zlib's output
+    std::vector<uint8_t> dev(total), tmp(65536 + 64);
+    CU_TRY(c, cudaMemcpy(dev.data(), d.d_inflated, total, cudaMemcpyDeviceToHost));
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    inflateInit2(&zs, -15);
+    uint32_t bad = 0;
+    for (uint32_t b = 0; b < nb; ++b) {
+      const uint32_t isz = in->block_isize[b];
+      if (!isz) continue;
+      if (tmp.size() < isz) tmp.resize(isz);
+      inflateReset(&zs);
+      zs.next_in = const_cast<Bytef*>(in->data + in->block_coffset[b]);
+      zs.avail_in = in->block_clen[b];
+      zs.next_out = tmp.data();
+      zs.avail_out = isz;
+      const int zr = inflate(&zs, Z_FINISH);
+      if (zr != Z_STREAM_END || memcmp(tmp.data(), dev.data() + ustart[b], isz) != 0) {
+        uint32_t k = 0;
+        while (k < isz && tmp[k] == dev[ustart[b] + k]) ++k;
+        if (bad < 8) fprintf(stderr, "#decode_verify\tblock %u (clen %u isize %u): zlib rc %d, first difference at byte %u\n", b, in->block_clen[b], isz, zr, k);
+        ++bad;
+      }
+    }
+    inflateEnd(&zs);
+    fprintf(stderr, "#decode_verify\t%u of %u blocks differ from zlib; %u inflated on the host\n", bad, nb, out->n_blocks_host);
+  }
+  // ---- record chain
+  WalkArgs wa{};
+  wa.data = d.d_inflated; wa.total = total; wa.ustart = d.d_ustart; wa.first_block = first_block; wa.n_blocks = nb;
+  wa.records_at = in->records_at; wa.n_ref = (int32_t)in->n_ref; wa.guess = d.d_guess; wa.exit_off = d.d_exit; wa.n_rec = d.d_nrec;
+  wa.n_cig = d.d_ncig; wa.dirty = d.d_dirty; wa.flags = d.d_cnt + 1; wa.only_dirty = 0;
+  const uint32_t nwb = nb - first_block;
+  CU_TRY(c, cudaMemsetAsync(d.d_dirty, 0, 4ull * nb, c->stream));
+  kd_guess<<<(nwb * 32 + 255) / 256, 256, 0, c->stream>>>(wa);
+  kd_walk<<<(nwb + 127) / 128, 128, 0, c->stream>>>(wa);
+  CU_TRY(c, cudaGetLastError());
+  uint64_t h_exit = 0;
+  for (uint32_t round = 0;; ++round) {
+    if (nwb > 1) {
+      CU_TRY(c, cudaMemsetAsync(d.d_cnt + 2, 0, 4, c->stream));
+      kd_verify<<<(nwb - 1 + 255) / 256, 256, 0, c->stream>>>(wa);
+      CU_TRY(c, cudaGetLastError());
+    }
+    CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(&h_exit, d.d_exit + (nb - 1), 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (nwb <= 1 || !h_cnt[2]) break;
+    if (round >= 256) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: record chain did not settle");
+    out->chain_repairs += 1;
+    wa.only_dirty = 1;
+    kd_walk<<<(nwb + 127) / 128, 128, 0, c->stream>>>(wa);
+    CU_TRY(c, cudaGetLastError());
+  }
+  if (h_exit != total) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: record chain does not end at the end of the stream");
+  kd_scan_items<<<1, 1024, 0, c->stream>>>(d.d_nrec, d.d_ncig, first_block, nb, d.d_rec_base, d.d_cig_base, (uint64_t*)(d.d_cnt + 6));
+  CU_TRY(c, cudaGetLastError());
+  uint64_t totals[2] = {0, 0};
+  CU_TRY(c, cudaMemcpyAsync(totals, d.d_cnt + 6, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  CU_TRY(c, cudaEventRecord(d.ev[3], c->stream));
+  const uint64_t n_rec = totals[0], n_cig = totals[1];
+  if (n_rec >= 0xffffff00ull || n_cig >= 0xffffff00ull) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: more than 2^32 records or cigar operations");
+  out->n_records = n_rec;
+  out->n_intervals = n_cig;
+  if (n_rec) {
+    if ((rc = dec_grow(c, d.d_rec_off, d.rec_cap, (size_t)n_rec))) return rc;
+    size_t offs[13];
+    const size_t need = batch_slab_bytes((uint32_t)n_rec, (uint32_t)n_cig, offs);
+    if (d.tuple_slab_bytes < need || !d.d_tuple_slab) {
+      cudaFree(d.d_tuple_slab);
+      d.d_tuple_slab = nullptr;
+      d.tuple_slab_bytes = 0;
+      const size_t want = need + need / 8;
+      CU_TRY(c, cudaMalloc(&d.d_tuple_slab, want));
+      d.tuple_slab_bytes = want;
+    }
+    cmb_read_batch tb;
+    carve_batch(d.d_tuple_slab, (uint32_t)n_rec, (uint32_t)n_cig, &tb);
+    OffsetArgs oa{};
+    oa.data = d.d_inflated; oa.ustart = d.d_ustart; oa.guess = d.d_guess; oa.rec_base = d.d_rec_base; oa.cig_base = d.d_cig_base;
+    oa.first_block = first_block; oa.n_blocks = nb; oa.rec_off = d.d_rec_off; oa.iv_begin = tb.iv_begin; oa.n_records = n_rec; oa.n_cig_total = n_cig;
+    kd_offsets<<<(nwb + 127) / 128, 128, 0, c->stream>>>(oa);
+    CU_TRY(c, cudaGetLastError());
+    ExtractArgs ea{};
+    ea.data = d.d_inflated; ea.rec_off = d.d_rec_off; ea.n_records = n_rec;
+    ea.tid = tb.tid; ea.pos = tb.pos; ea.flag = tb.flag; ea.mapq = tb.mapq; ea.nm_state = tb.nm_state; ea.nm = tb.nm; ea.l_seq = tb.l_seq;
+    ea.aligned = tb.aligned; ea.del = tb.del; ea.ins = tb.ins; ea.iv_begin = tb.iv_begin; ea.iv_start = tb.iv_start; ea.iv_len = tb.iv_len;
+    ea.n_primary = (unsigned long long*)(d.d_cnt + 4); ea.flags = d.d_cnt + 1;
+    kd_extract<<<(uint32_t)((n_rec + 255) / 256), 256, 0, c->stream>>>(ea);
+    CU_TRY(c, cudaGetLastError());
+    CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    if (h_cnt[1]) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: malformed alignment record (flags %u)", h_cnt[1]);
+    memcpy(&out->n_primary, h_cnt + 4, 8);
+    CU_TRY(c, cudaEventRecord(d.ev[4], c->stream));
+    if (c->n_local) {
+      rc = launch_k1(c, tb, (uint32_t)n_rec, (uint32_t)n_cig);
+      if (rc) return rc;
+    }
+  } else {
+    CU_TRY(c, cudaEventRecord(d.ev[4], c->stream));
+  }
+  CU_TRY(c, cudaEventRecord(d.ev[5], c->stream));
+  CU_TRY(c, cudaEventSynchronize(d.ev[4]));
+  cudaEventElapsedTime(&out->ms_copy_inflate, d.ev[0], d.ev[2]);
+  cudaEventElapsedTime(&out->ms_chain, d.ev[2], d.ev[3]);
+  cudaEventElapsedTime(&out->ms_extract, d.ev[3], d.ev[4]);
+  cudaEventElapsedTime(&out->ms_total, d.ev[0], d.ev[4]);
+  return CMB_OK;
+}

@@ -305,6 +305,45 @@ class DeviceSession {
       BlockIndex bx;
       if (stream.is_raw()) bx.build(stream.raw_data(), stream.raw_size());
       else bx.build(p, n);
+      // Device-side decode first (compressed blocks cross PCIe, the GPU inflates and parses them); the host pipeline
+      // below runs when the input is not BGZF, when CMB_HOST_DECODE is set, or when the device declines the stream.
+      bool decoded_on_device = false;
+      if (bx.bgzf && !stream.is_raw() && !getenv("CMB_HOST_DECODE")) {
+        const size_t nb = bx.blocks.size();
+        std::vector<uint64_t> coff(nb);
+        std::vector<uint32_t> clen(nb), isz(nb);
+        for (size_t b = 0; b < nb; ++b) {
+          coff[b] = bx.blocks[b].cdata;
+          clen[b] = (uint32_t)bx.blocks[b].clen;
+          isz[b] = bx.blocks[b].isize;
+        }
+        cmb_bgzf_input bi{};
+        bi.data = p;
+        bi.size = n;
+        bi.n_blocks = (uint32_t)nb;
+        bi.n_ref = n_ref;
+        bi.block_coffset = coff.data();
+        bi.block_clen = clen.data();
+        bi.block_isize = isz.data();
+        bi.records_at = records_at;
+        bi.copy_threads = (uint32_t)std::min(pool_.size(), 8);
+        cmb_bgzf_result br{};
+        const double a = now_s();
+        const int r2 = cmb_submit_bgzf(ctx_, &bi, &br);
+        if (r2 == CMB_OK) {
+          decoded_on_device = true;
+          res.n_records = br.n_records;
+          res.num_detected_primary_alignments = br.n_primary;
+          if (getenv("CMB_PIPELINE_STATS"))
+            fprintf(stderr, "#device_decode\tblocks=%zu\thost_blocks=%u\trepairs=%u\tcopy_inflate_ms=%.2f\tchain_ms=%.2f\textract_ms=%.2f\ttotal_ms=%.2f\tcall_s=%.4f\n",
+                    nb, br.n_blocks_host, br.chain_repairs, br.ms_copy_inflate, br.ms_chain, br.ms_extract, br.ms_total, now_s() - a);
+        } else if (r2 != CMB_E_DECLINED) {
+          throw_device_error(ctx_, r2);
+        } else if (getenv("CMB_PIPELINE_STATS")) {
+          fprintf(stderr, "#device_decode\tdeclined: %s\n", cmb_last_error(ctx_));
+        }
+      }
+      if (!decoded_on_device) {
       const PipelineCounts pc = run_decode_pipeline(
           bx, records_at, n_ref, pool_.size(), batch_records_, batch_intervals_, n_staging_, scratch_,
           [&](cmb_read_batch* b) {
@@ -324,6 +363,7 @@ class DeviceSession {
       if (getenv("CMB_PIPELINE_STATS"))
         fprintf(stderr, "#pipeline\titems=%u\tworkers=%u\tinflate_s=%.3f\tchain_s=%.3f\textract_s=%.3f\tidle_s=%.3f (summed over workers)\n",
                 pc.n_items, pc.n_workers, pc.inflate_s, pc.scan_s, pc.extract_s, pc.idle_s);
+      }
     } else for (;;) {
       // complete records currently in buf
       rec_off.clear();

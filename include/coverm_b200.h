@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CMB_ABI_VERSION 1
+#define CMB_ABI_VERSION 2
 
 /* error codes */
 #define CMB_OK 0
@@ -51,6 +51,8 @@ extern "C" {
 #define CMB_E_NM (-5)        /* NM aux missing / wrong type where the reference calls nm()  (lib.rs:138-158 panic) */
 #define CMB_E_BOUNDS (-6)    /* an aligned block starts at/after the contig end (contig.rs:178 index panic) */
 #define CMB_E_CAPACITY (-7)  /* a device-side buffer (histogram records) overflowed         */
+#define CMB_E_DECLINED (-8)  /* cmb_submit_bgzf: the device decoder cannot vouch for this stream; nothing was
+                                accumulated -- decode on the host instead                    */
 
 typedef struct cmb_ctx cmb_ctx;
 
@@ -198,6 +200,37 @@ int cmb_fetch_pairs(cmb_ctx* ctx, cmb_hist_pair* pairs, uint64_t n_pairs);
 /* Same, but leaves the rows in device memory (no D2H): *dev_stats is a device pointer to n_contigs rows,
  * valid until the next cmb_begin_sample.  For device-only timing and for NCCL all-gather by the caller. */
 int cmb_end_sample_device(cmb_ctx* ctx, const cmb_contig_stats** dev_stats);
+
+/* ---- Device-side BAM decode (optional fast path; the step before the path, bam_generator.rs:103-134) ----
+ * Instead of tuples, hand the library the BGZF-compressed BAM bytes of the sample plus its block table: the GPU
+ * inflates the blocks, finds the record boundaries, extracts the tuples and runs the same filter/delta kernel.
+ * Call it between cmb_begin_sample and cmb_end_sample INSTEAD of the acquire/submit loop, and only when
+ * cmb_filter_mode.filter_pairs == 0 (mate matching needs read names, which never reach the device).
+ * Returns CMB_E_DECLINED -- with nothing accumulated -- when the device path cannot vouch for the stream (malformed
+ * deflate data, an inconsistent record chain, an unknown aux type ...): the caller then decodes on the host, which
+ * raises the reference's error if there is one.  `data` may be pageable (staged through pinned buffers by
+ * `copy_threads` host threads) or pinned / registered memory (copied directly). */
+typedef struct cmb_bgzf_input {
+  const uint8_t* data;            /* host pointer: the whole BAM file                                  */
+  uint64_t size;
+  uint32_t n_blocks;
+  uint32_t n_ref;                 /* header n_ref, for record plausibility                             */
+  const uint64_t* block_coffset;  /* per BGZF block: offset of its deflate payload in `data`           */
+  const uint32_t* block_clen;     /* payload length (the 8-byte CRC32/ISIZE footer follows it)         */
+  const uint32_t* block_isize;    /* uncompressed size                                                 */
+  uint64_t records_at;            /* uncompressed offset of the first alignment record                 */
+  uint32_t copy_threads;          /* 0 = 4                                                             */
+  uint32_t reserved;
+} cmb_bgzf_input;
+typedef struct cmb_bgzf_result {
+  uint64_t n_records;             /* alignment records in the file                                     */
+  uint64_t n_primary;             /* ... neither secondary nor supplementary (bam_generator.rs:113-119) */
+  uint64_t n_intervals;           /* interval slots reserved (sum of n_cigar_op)                       */
+  uint32_t n_blocks_host;         /* blocks the device declined and the library inflated with zlib     */
+  uint32_t chain_repairs;         /* record-chain repair rounds                                        */
+  float ms_copy_inflate, ms_chain, ms_extract, ms_total; /* CUDA events on the ctx stream              */
+} cmb_bgzf_result;
+int cmb_submit_bgzf(cmb_ctx* ctx, const cmb_bgzf_input* in, cmb_bgzf_result* out);
 
 int cmb_get_timing(const cmb_ctx* ctx, cmb_sample_timing* out);
 /* cudaStream_t of the context (as void*), for callers that order their own work after it. */

@@ -11,7 +11,7 @@ ORACLE_BIN = os.path.join(ROOT, "oracle", "coverm_oracle")
 PRODUCT_BIN = os.path.join(ROOT, "coverm_b200", "bin", "coverm")
 
 
-def run_case(binary, case, extra_args=(), timeout=300):
+def run_case(binary, case, extra_args=(), timeout=300, env=None):
     with tempfile.TemporaryDirectory() as td:
         defpath = os.path.join(td, "genome.definition")
         if "definition" in case:
@@ -19,7 +19,7 @@ def run_case(binary, case, extra_args=(), timeout=300):
                 f.write(case["definition"])
         argv = [a.replace("{D}", DATA).replace("{DEF}", defpath) for a in case["argv"]]
         p = subprocess.run([binary, case["sub"]] + argv + list(extra_args), capture_output=True, text=True,
-                           timeout=timeout)
+                           timeout=timeout, env=dict(os.environ, **(env or {})))
     return p
 
 

@@ -24,16 +24,16 @@ def test_cuda_path_matches_reference_golden(case):
 
 
 # ---------------------------------------------------------------------------------------------- GPU vs oracle
-def _both(argv, threads="8"):
+def _both(argv, threads="8", env=None):
     g = subprocess.run([coverm_b200.COVERM_BIN] + argv + ["-t", threads, "--print-reads-mapped"], capture_output=True,
-                       text=True, timeout=900)
+                       text=True, timeout=900, env=dict(os.environ, **(env or {})))
     o = subprocess.run([ORACLE_BIN] + argv + ["-t", threads, "--print-reads-mapped"], capture_output=True, text=True,
                        timeout=900)
     return g, o
 
 
-def _assert_same(argv):
-    g, o = _both(argv)
+def _assert_same(argv, env=None):
+    g, o = _both(argv, env=env)
     assert g.returncode == o.returncode, f"{argv}: exit {g.returncode} vs oracle {o.returncode}\n{g.stderr[-1500:]}"
     if g.stdout != o.stdout:
         gl, ol = g.stdout.splitlines(), o.stdout.splitlines()
@@ -41,6 +41,7 @@ def _assert_same(argv):
         raise AssertionError(f"{argv}: {len(gl)} vs {len(ol)} lines; first differences (line, gpu, oracle): {diff}")
     rm = lambda p: [l for l in p.stderr.splitlines() if l.startswith("#reads_mapped")]
     assert rm(g) == rm(o)
+    return g
 
 
 ALL_METHODS = ["mean", "trimmed_mean", "covered_fraction", "covered_bases", "variance", "length", "count",
@@ -115,6 +116,48 @@ SYNTH_RUNS = [
 def test_cuda_path_matches_oracle_on_synthetic_bams(synth, which, argv):
     argv = [a.replace("{mags_def}", synth["mags_def"]) for a in argv]
     _assert_same(argv + ["-b", synth[which]])
+
+
+# ---------------------------------------------------------------------------------------------- decode paths
+# BGZF inputs are decoded on the GPU by default (kd_inflate ... kd_extract); CMB_HOST_DECODE=1 forces the host decoder.
+DECODE_FIXTURES = ["2seqs.reads_for_seq1.bam", "7seqs.reads_for_seq1_and_seq2.bam", "1.bam", "eg2.bam", "1read_of_pair_mapped.bam",
+                   "k141_2005182.bam", "2seqs.bad_read.1.with_supplementary.bam", "tpm_test.bam"]
+
+
+def _decode_stats(g):
+    lines = [l for l in g.stderr.splitlines() if l.startswith("#device_decode") or l.startswith("#decode_verify")]
+    return lines
+
+
+@pytest.mark.parametrize("name", DECODE_FIXTURES)
+def test_device_inflate_matches_zlib_on_reference_fixtures(name):
+    g = _assert_same(["contig", "-m", "mean", "trimmed_mean", "variance", "count", "-b", os.path.join(DATA, name)],
+                     env={"CMB_PIPELINE_STATS": "1", "CMB_DECODE_VERIFY": "1"})
+    st = _decode_stats(g)
+    assert any(l.startswith("#device_decode\tblocks=") for l in st), st  # the device path ran and was not declined
+    assert any(l.startswith("#decode_verify\t0 of ") for l in st), st     # every device-inflated block equals zlib's output
+
+
+@pytest.mark.parametrize("which", ["small", "tiny", "long", "deep", "mags"])
+def test_device_inflate_matches_zlib_on_synthetic_bams(synth, which):
+    g = _assert_same(["contig", "-m", "mean", "trimmed_mean", "count", "-b", synth[which]],
+                     env={"CMB_PIPELINE_STATS": "1", "CMB_DECODE_VERIFY": "1"})
+    st = _decode_stats(g)
+    assert any(l.startswith("#device_decode\tblocks=") and "host_blocks=0" in l for l in st), st
+    assert any(l.startswith("#decode_verify\t0 of ") for l in st), st
+
+
+@pytest.mark.parametrize("which,argv", [SYNTH_RUNS[0], SYNTH_RUNS[2], SYNTH_RUNS[10], SYNTH_RUNS[14]],
+                         ids=["small-all", "small-filter", "long-all", "mags-genome"])
+def test_host_decode_path_matches_oracle(synth, which, argv):
+    argv = [a.replace("{mags_def}", synth["mags_def"]) for a in argv]
+    g = _assert_same(argv + ["-b", synth[which]], env={"CMB_HOST_DECODE": "1", "CMB_PIPELINE_STATS": "1"})
+    assert any(l.startswith("#pipeline") for l in g.stderr.splitlines())
+
+
+def test_host_decode_path_matches_reference_goldens():
+    for case in GPU_CASES[:12]:
+        check_case(case, run_case(coverm_b200.COVERM_BIN, case, extra_args=["-t", "4"], env={"CMB_HOST_DECODE": "1"}))
 
 
 def test_multiple_samples_reuse_the_arena(synth):
