@@ -77,7 +77,9 @@ class SampleInfo(C.Structure):
                 ("end_sample_s", C.c_double), ("k0_ms", C.c_float), ("k1_ms", C.c_float), ("k2_ms", C.c_float),
                 ("k3_ms", C.c_float), ("device_total_ms", C.c_float), ("k1_launches", C.c_uint32),
                 ("k2_launches", C.c_uint32), ("k3_launches", C.c_uint32), ("arena_elems", C.c_uint64),
-                ("n_intervals", C.c_uint64)]
+                ("n_intervals", C.c_uint64), ("h2d_bytes", C.c_uint64), ("device_decode", C.c_uint32),
+                ("decode_host_blocks", C.c_uint32), ("decode_copy_inflate_ms", C.c_float), ("decode_chain_ms", C.c_float),
+                ("decode_extract_ms", C.c_float), ("decode_launches", C.c_uint32)]
 
 
 class HostResult(C.Structure):
@@ -88,7 +90,7 @@ class HostResult(C.Structure):
 DEVICE_SYMBOLS = ["cmb_abi_version", "cmb_create", "cmb_destroy", "cmb_last_error", "cmb_set_reference",
                   "cmb_set_params", "cmb_begin_sample", "cmb_acquire_batch", "cmb_submit_batch",
                   "cmb_submit_device_batch", "cmb_submit_bgzf", "cmb_end_sample", "cmb_fetch_pairs", "cmb_end_sample_device",
-                  "cmb_get_timing", "cmb_stream"]
+                  "cmb_get_timing", "cmb_stream", "cmb_host_alloc", "cmb_host_free"]
 class Tuples(C.Structure):
     _fields_ = [("n_contigs", C.c_uint32), ("contig_len", C.POINTER(C.c_uint64)), ("n_records", C.c_uint64),
                 ("n_intervals", C.c_uint64), ("tid", C.POINTER(C.c_int32)), ("pos", C.POINTER(C.c_int32)),
@@ -168,8 +170,18 @@ def load_library(path=None):
 
 
 class RunResult:
-    def __init__(self, status, out, err, samples):
-        self.status, self.out, self.err, self.samples = status, out, err, samples
+    """status / stdout / stderr of one in-process `coverm` run.  ``out_bytes`` is the table exactly as the C ABI returned
+    it; ``out`` decodes it to str on first use."""
+
+    def __init__(self, status, out_bytes, err, samples):
+        self.status, self.out_bytes, self.err, self.samples = status, out_bytes, err, samples
+        self._out = None
+
+    @property
+    def out(self):
+        if self._out is None:
+            self._out = self.out_bytes.decode()
+        return self._out
 
 
 class Session:
@@ -211,7 +223,7 @@ class Session:
         rc = lib.cmbh_run(self._h, len(argv), args, mem, n_mem, C.byref(res))
         if rc != 0:
             raise CmbError(f"cmbh_run failed with {rc}")
-        out = C.string_at(res.out, res.out_len).decode() if res.out else ""
+        out = C.string_at(res.out, res.out_len) if res.out else b""
         err = C.string_at(res.err, res.err_len).decode() if res.err else ""
         samples = []
         for i in range(res.n_samples):

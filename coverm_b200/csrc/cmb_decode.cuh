@@ -20,7 +20,7 @@
 // ------------------------------------------------------------------------------------------------ KD1 inflate
 constexpr uint32_t INF_WARPS = 16;  // warps per CTA
 constexpr uint32_t INF_ROOT = 10, INF_SUBBITS = 5;
-constexpr uint32_t INF_SUBQ = 64;  // distinct root-bit prefixes of codes longer than the root
+constexpr uint32_t INF_SUBQ = 128;  // distinct root-bit prefixes of codes longer than the root
 constexpr uint32_t INF_LIT_ENTRIES = (1u << INF_ROOT) + 512;  // zlib's ENOUGH bound for (286, root 10, max 15) is 1024 + 308
 constexpr uint32_t INF_DST_ENTRIES = (1u << INF_ROOT) + 128;
 constexpr uint32_t INF_OK = 0, INF_DECLINED = 1;
@@ -125,8 +125,7 @@ __device__ bool inf_build_table(InfWarpSmem& S, const uint8_t* lens, uint32_t n,
   if (over) return false;
   const uint32_t P0 = __shfl_sync(FULL, my_first, root + 1) >> 1;
   if (lane < 16) S.nc[lane] = my_first;
-  S.subq[lane] = 0;
-  S.subq[lane + 32] = 0;
+  for (uint32_t q = lane; q < INF_SUBQ; q += 32) S.subq[q] = 0;
   if (lane == 0) S.overflow = 0;
   __syncwarp();
   const uint32_t root_size = 1u << root;

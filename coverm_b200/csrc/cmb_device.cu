@@ -33,6 +33,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <atomic>
+#include <chrono>
 #include <string>
 #include <thread>
 #include <vector>
@@ -718,6 +719,18 @@ int cmb_get_timing(const cmb_ctx* c, cmb_sample_timing* out) {
 
 void* cmb_stream(cmb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+void* cmb_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  return p;
+}
+void cmb_host_free(void* p) {
+  if (p) cudaFreeHost(p);
+}
+
 }  // extern "C"
 
 // ------------------------------------------------------------------------------------------------ device-side decode
@@ -817,7 +830,6 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   cudaGetLastError();  // cudaPointerGetAttributes on pageable memory may leave a sticky-free error code
   uint32_t T = in->copy_threads ? in->copy_threads : 4;
   T = std::min<uint32_t>(std::min<uint32_t>(T, 16), (uint32_t)windows.size());
-  if (src_pinned) T = std::min<uint32_t>(T, 2);
   while (d.streams.size() < T) {
     cudaStream_t st;
     CU_TRY(c, cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
@@ -888,15 +900,40 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
     }
     check(cudaEventRecord(d.done_events[t], st));
   };
+  const auto copy_t0 = std::chrono::steady_clock::now();
   {
     std::vector<std::thread> threads;
     for (uint32_t t = 1; t < T; ++t) threads.emplace_back(worker, t);
     worker(0);
     for (auto& th : threads) th.join();
   }
+  const double copy_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - copy_t0).count();
+  (void)copy_wall_ms;
+  out->n_launches = (uint32_t)windows.size();
+  out->h2d_bytes = in->size + 24ull * nb + 8;
   if (first_err.load()) return fail(c, CMB_E_CUDA, "cmb_submit_bgzf: copy/inflate stage failed: %s", cudaGetErrorString((cudaError_t)first_err.load()));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(c->stream, d.done_events[t], 0));
   CU_TRY(c, cudaEventRecord(d.ev[2], c->stream));
+  if (getenv("CMB_DECODE_PROFILE")) {  // debugging aid: the inflate kernel alone, all blocks resident, one launch
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    cudaEvent_t p0, p1;
+    cudaEventCreate(&p0);
+    cudaEventCreate(&p1);
+    CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4, c->stream));
+    InflateArgs a{};
+    a.comp = d.d_comp; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
+    a.b0 = 0; a.b1 = nb; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 8;
+    cudaEventRecord(p0, c->stream);
+    kd_inflate<<<std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)c->sm_count * 2), INF_WARPS * 32, INF_SMEM_BYTES, c->stream>>>(a);
+    cudaEventRecord(p1, c->stream);
+    CU_TRY(c, cudaStreamSynchronize(c->stream));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, p0, p1);
+    fprintf(stderr, "#decode_profile\tinflate_only_ms=%.3f\tblocks=%u\tcompressed=%llu\tinflated=%llu\tinflated_GBps=%.2f\tcopy_threads=%u\tsrc_pinned=%d\tcopy_enqueue_wall_ms=%.2f\n", ms, nb,
+            (unsigned long long)in->size, (unsigned long long)total, total / ms * 1e-6, T, (int)src_pinned, copy_wall_ms);
+    cudaEventDestroy(p0);
+    cudaEventDestroy(p1);
+  }
   // ---- blocks the device declined: zlib on the host, patched into the inflated stream
   uint32_t h_cnt[16];
   CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
@@ -973,12 +1010,14 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   kd_guess<<<(nwb * 32 + 255) / 256, 256, 0, c->stream>>>(wa);
   kd_walk<<<(nwb + 127) / 128, 128, 0, c->stream>>>(wa);
   CU_TRY(c, cudaGetLastError());
+  out->n_launches += 2;
   uint64_t h_exit = 0;
   for (uint32_t round = 0;; ++round) {
     if (nwb > 1) {
       CU_TRY(c, cudaMemsetAsync(d.d_cnt + 2, 0, 4, c->stream));
       kd_verify<<<(nwb - 1 + 255) / 256, 256, 0, c->stream>>>(wa);
       CU_TRY(c, cudaGetLastError());
+      out->n_launches += 1;
     }
     CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaMemcpyAsync(&h_exit, d.d_exit + (nb - 1), 8, cudaMemcpyDeviceToHost, c->stream));
@@ -986,6 +1025,7 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
     if (nwb <= 1 || !h_cnt[2]) break;
     if (round >= 256) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: record chain did not settle");
     out->chain_repairs += 1;
+    out->n_launches += 1;
     wa.only_dirty = 1;
     kd_walk<<<(nwb + 127) / 128, 128, 0, c->stream>>>(wa);
     CU_TRY(c, cudaGetLastError());
@@ -993,6 +1033,7 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   if (h_exit != total) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: record chain does not end at the end of the stream");
   kd_scan_items<<<1, 1024, 0, c->stream>>>(d.d_nrec, d.d_ncig, first_block, nb, d.d_rec_base, d.d_cig_base, (uint64_t*)(d.d_cnt + 6));
   CU_TRY(c, cudaGetLastError());
+  out->n_launches += 1;
   uint64_t totals[2] = {0, 0};
   CU_TRY(c, cudaMemcpyAsync(totals, d.d_cnt + 6, 16, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1027,6 +1068,7 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
     ea.n_primary = (unsigned long long*)(d.d_cnt + 4); ea.flags = d.d_cnt + 1;
     kd_extract<<<(uint32_t)((n_rec + 255) / 256), 256, 0, c->stream>>>(ea);
     CU_TRY(c, cudaGetLastError());
+    out->n_launches += 2;
     CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     if (h_cnt[1]) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: malformed alignment record (flags %u)", h_cnt[1]);

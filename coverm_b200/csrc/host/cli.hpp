@@ -332,6 +332,7 @@ inline CliResult run_cli(const std::vector<std::string>& args, const std::vector
       session = own.get();
     }
     plan.printer.pool = &session->pool();
+    const double t_driver0 = now_s();
     DriverIO io{session, plan.params, &res.timings, &res.record_counts};
     if (o.sub == "contig") {
       res.reads_mapped = contig_coverage(inputs, taker, plan.estimators, !o.no_zeros, io);
@@ -351,8 +352,10 @@ inline CliResult run_cli(const std::vector<std::string>& args, const std::vector
         res.reads_mapped = mosdepth_genome_coverage_with_contig_names(inputs, gc, taker, !o.no_zeros, plan.estimators, io);
       }
     }
+    const double t_print0 = now_s();
     plan.printer.finalise_printing(taker, *os, res.reads_mapped, plan.columns_to_normalise, plan.rpkm_column, plan.tpm_column);
     os->flush();
+    if (o.timing) err << "#timing_run\tdrivers_s=" << (t_print0 - t_driver0) << "\tprint_s=" << (now_s() - t_print0) << '\n';
     if (o.print_reads_mapped)
       for (size_t i = 0; i < res.reads_mapped.size(); ++i)
         err << "#reads_mapped\t" << file_stem(o.bam_files[i]) << '\t' << res.reads_mapped[i].num_mapped_reads << '\t'

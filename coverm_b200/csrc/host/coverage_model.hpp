@@ -61,6 +61,12 @@ class CoverageTaker {  // coverage_takers.rs:29-38 (trait) over the three Covera
   static CoverageTaker pileup(std::ostream* o) { CoverageTaker t; t.kind = Kind::PileupStreaming; t.out = o; return t; }
   static CoverageTaker cached(size_t n) { CoverageTaker t; t.kind = Kind::CachedSingleFloat; t.num_coverages = n; return t; }
 
+  // Capacity hint (cached taker): n_entries entries of k coverages are about to be added to the current stoit.
+  void reserve_entries(size_t n_entries, size_t k) {
+    if (kind != Kind::CachedSingleFloat) return;
+    if (entry_names.size() < n_entries) entry_names.resize(n_entries);
+    coverages[cur_stoit_index_].reserve(coverages[cur_stoit_index_].size() + n_entries * k);
+  }
   void start_stoit(const std::string& name) {
     if (kind == Kind::CachedSingleFloat) {
       stoit_names.push_back(name);

@@ -131,6 +131,55 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
     const uint32_t n = (uint32_t)r.header.names.size();
     std::vector<float> coverages(coverage_estimators.size());
     const std::vector<uint64_t> contig_mode_unobserved{0};  // calculate_coverage(&[0]), contig.rs:65
+    bool any_pileup = false;
+    for (auto& e : coverage_estimators) any_pileup = any_pileup || e.kind == CoverageEstimator::Kind::PileupCounts;
+    if (!any_pileup && n >= 1024) {
+      // Same per-contig sequence as the loop below (add_contig, calculate_coverage(&[0]), setup), but contigs are
+      // independent, so the estimator maths runs on all host threads into a table; the taker is then fed in tid order.
+      const size_t K = coverage_estimators.size();
+      std::vector<float> vals((size_t)n * K);
+      std::vector<uint8_t> state(n, 0);  // 0: never seen, 1: seen, all coverages zero, 2: seen, some coverage > 0
+      ThreadPool& pool = io.session->pool();
+      const size_t n_tasks = std::min<size_t>((size_t)pool.size() * 4, (n + 4095) / 4096);
+      std::vector<uint64_t> task_mapped(n_tasks, 0);
+      pool.parallel_for(n_tasks, [&](size_t task, int) {
+        std::vector<CoverageEstimator> est = coverage_estimators;
+        const uint32_t t0 = (uint32_t)((uint64_t)n * task / n_tasks), t1 = (uint32_t)((uint64_t)n * (task + 1) / n_tasks);
+        uint64_t mapped = 0;
+        for (uint32_t tid = t0; tid < t1; ++tid) {
+          if (r.rows[tid].n_records == 0) continue;
+          const ContigObservation ob = observe(r, tid, CountMode::Contig, csr);
+          bool has_nonzero = false;
+          for (size_t k = 0; k < K; ++k) {
+            est[k].add_contig(ob);
+            const float c = est[k].calculate_coverage(contig_mode_unobserved);
+            vals[(size_t)tid * K + k] = c;
+            has_nonzero = has_nonzero || c > 0.0f;
+            est[k].setup();
+          }
+          state[tid] = has_nonzero ? 2 : 1;
+          if (has_nonzero) mapped += ob.num_mapped_reads;
+        }
+        task_mapped[task] = mapped;
+      });
+      for (uint64_t m : task_mapped) num_mapped_reads_total += m;
+      coverage_taker.reserve_entries(n, K);
+      for (uint32_t tid = 0; tid < n; ++tid) {
+        if (state[tid] == 0) {
+          if (print_zero_coverage_contigs) {
+            coverage_taker.start_entry(tid, r.header.names[tid]);
+            for (auto& e : coverage_estimators) e.print_zero_coverage(coverage_taker, r.header.lens[tid]);
+            coverage_taker.finish_entry();
+          }
+        } else if (print_zero_coverage_contigs || state[tid] == 2) {
+          coverage_taker.start_entry(tid, r.header.names[tid]);
+          for (size_t k = 0; k < K; ++k) coverage_estimators[k].print_coverage(vals[(size_t)tid * K + k], coverage_taker);
+          coverage_taker.finish_entry();
+        }
+      }
+      reads_mapped_vector.push_back({num_mapped_reads_total, r.num_detected_primary_alignments});
+      continue;
+    }
     for (uint32_t tid = 0; tid < n; ++tid) {
       if (r.rows[tid].n_records == 0) {  // never seen: print_previous_zero_coverage_contigs (:255-277)
         if (print_zero_coverage_contigs) {

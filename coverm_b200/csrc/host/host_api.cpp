@@ -91,6 +91,13 @@ int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_
     si.k3_launches = t.device.k3_launches;
     si.arena_elems = t.device.arena_elems;
     si.n_intervals = t.device.n_intervals;
+    si.h2d_bytes = t.h2d_bytes;
+    si.device_decode = t.device_decode ? 1u : 0u;
+    si.decode_host_blocks = t.bgzf.n_blocks_host;
+    si.decode_copy_inflate_ms = t.bgzf.ms_copy_inflate;
+    si.decode_chain_ms = t.bgzf.ms_chain;
+    si.decode_extract_ms = t.bgzf.ms_extract;
+    si.decode_launches = t.decode_launches;
   }
   return 0;
 }

@@ -25,12 +25,16 @@ inline std::string file_stem(const std::string& path) {  // Path::file_stem (bam
 struct SampleTiming {
   double total_s = 0, decode_s = 0, submit_wait_s = 0, end_sample_s = 0;
   cmb_sample_timing device{};
+  uint64_t h2d_bytes = 0;
+  bool device_decode = false;
+  cmb_bgzf_result bgzf{};
+  uint32_t decode_launches = 0;
 };
 
 struct SampleResult {
   std::string stoit_name;
   Header header;
-  std::vector<cmb_contig_stats> rows;
+  const cmb_contig_stats* rows = nullptr;  // n_ref rows in the session's page-locked buffer; valid until the next process()
   std::vector<cmb_hist_pair> pairs;
   uint64_t num_detected_primary_alignments = 0;  // bam_generator.rs:113-119 / filter.rs:94-96,129-131
   uint64_t n_records = 0;                        // every record read from the file
@@ -181,7 +185,10 @@ class DeviceSession {
     batch_intervals_ = cfg.batch_intervals;
     n_staging_ = cfg.n_staging;
   }
-  ~DeviceSession() { cmb_destroy(ctx_); }
+  ~DeviceSession() {
+    cmb_host_free(rows_buf_);
+    cmb_destroy(ctx_);
+  }
   DeviceSession(const DeviceSession&) = delete;
   ThreadPool& pool() { return pool_; }
   cmb_ctx* ctx() { return ctx_; }
@@ -332,6 +339,10 @@ class DeviceSession {
         const int r2 = cmb_submit_bgzf(ctx_, &bi, &br);
         if (r2 == CMB_OK) {
           decoded_on_device = true;
+          res.timing.device_decode = true;
+          res.timing.bgzf = br;
+          res.timing.h2d_bytes = br.h2d_bytes;
+          res.timing.decode_launches = br.n_launches;
           res.n_records = br.n_records;
           res.num_detected_primary_alignments = br.n_primary;
           if (getenv("CMB_PIPELINE_STATS"))
@@ -439,9 +450,16 @@ class DeviceSession {
     }
     const double t_dec = now_s();
     submit();
-    res.rows.resize(n_ref);
+    if (rows_cap_ < (size_t)n_ref + 1) {
+      cmb_host_free(rows_buf_);
+      rows_cap_ = 0;
+      rows_buf_ = (cmb_contig_stats*)cmb_host_alloc(sizeof(cmb_contig_stats) * ((size_t)n_ref + 1));
+      if (!rows_buf_) throw ExitError(1, "cannot allocate the page-locked result buffer");
+      rows_cap_ = (size_t)n_ref + 1;
+    }
+    res.rows = rows_buf_;
     uint64_t n_pairs = 0;
-    rc = cmb_end_sample(ctx_, res.rows.data(), nullptr, 0, &n_pairs);
+    rc = cmb_end_sample(ctx_, rows_buf_, nullptr, 0, &n_pairs);
     if (rc) throw_device_error(ctx_, rc);
     if ((params.want & CMB_WANT_HIST_CSR) && n_pairs) {
       res.pairs.resize(n_pairs);
@@ -449,6 +467,7 @@ class DeviceSession {
       if (rc) throw_device_error(ctx_, rc);
     }
     cmb_get_timing(ctx_, &res.timing.device);
+    if (!res.timing.device_decode) res.timing.h2d_bytes = 40ull * res.timing.device.n_records + 4 + 8ull * res.timing.device.n_intervals;
     const double t1 = now_s();
     res.timing.total_s = t1 - t0;
     res.timing.decode_s = t_dec - t0 - wait_s;
@@ -458,6 +477,8 @@ class DeviceSession {
   }
 
  private:
+  cmb_contig_stats* rows_buf_ = nullptr;
+  size_t rows_cap_ = 0;
   ThreadPool pool_;
   DecodeScratch scratch_;
   cmb_ctx* ctx_ = nullptr;

@@ -229,8 +229,16 @@ typedef struct cmb_bgzf_result {
   uint32_t n_blocks_host;         /* blocks the device declined and the library inflated with zlib     */
   uint32_t chain_repairs;         /* record-chain repair rounds                                        */
   float ms_copy_inflate, ms_chain, ms_extract, ms_total; /* CUDA events on the ctx stream              */
+  uint32_t n_launches;            /* decode kernels launched (inflate windows + chain + extract)       */
+  uint32_t reserved;
+  uint64_t h2d_bytes;             /* compressed bytes + block table copied host->device                */
 } cmb_bgzf_result;
 int cmb_submit_bgzf(cmb_ctx* ctx, const cmb_bgzf_input* in, cmb_bgzf_result* out);
+
+/* Page-locked host memory for result buffers (cmb_end_sample copies straight into it at PCIe speed).  Plain malloc
+ * semantics otherwise; free with cmb_host_free. */
+void* cmb_host_alloc(size_t bytes);
+void cmb_host_free(void* p);
 
 int cmb_get_timing(const cmb_ctx* ctx, cmb_sample_timing* out);
 /* cudaStream_t of the context (as void*), for callers that order their own work after it. */

@@ -36,6 +36,11 @@ typedef struct cmbh_sample_info {
   float k0_ms, k1_ms, k2_ms, k3_ms, device_total_ms;
   uint32_t k1_launches, k2_launches, k3_launches;
   uint64_t arena_elems, n_intervals;
+  uint64_t h2d_bytes;        /* bytes copied host->device for this sample: tuples (host decode) or BGZF bytes + block table */
+  uint32_t device_decode;    /* 1: the GPU inflated and parsed the BAM (cmb_submit_bgzf); 0: host decode pipeline */
+  uint32_t decode_host_blocks; /* BGZF blocks the device declined (inflated with zlib by the library) */
+  float decode_copy_inflate_ms, decode_chain_ms, decode_extract_ms; /* device decode stages (CUDA events) */
+  uint32_t decode_launches;  /* kernels launched by the device decode */
 } cmbh_sample_info;
 
 typedef struct cmbh_result {

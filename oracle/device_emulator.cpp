@@ -196,6 +196,8 @@ int cmb_submit_batch(cmb_ctx* c, uint32_t n, uint32_t ni) {
   return submit(c, c->batches[i], n, ni);
 }
 int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* b, uint32_t n, uint32_t ni) { return submit(c, *b, n, ni); }
+void* cmb_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
+void cmb_host_free(void* p) { free(p); }
 // The emulator has no device-side decoder: always decline, so the host decode pipeline is what the CPU tests exercise.
 int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input*, cmb_bgzf_result*) {
   if (c) c->err = "device emulator: no device-side decode";

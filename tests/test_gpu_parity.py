@@ -125,7 +125,7 @@ DECODE_FIXTURES = ["2seqs.reads_for_seq1.bam", "7seqs.reads_for_seq1_and_seq2.ba
 
 
 def _decode_stats(g):
-    lines = [l for l in g.stderr.splitlines() if l.startswith("#device_decode") or l.startswith("#decode_verify")]
+    lines = [l for l in g.stderr.splitlines() if l.startswith("#device_decode") or l.startswith("#decode_")]
     return lines
 
 

@@ -24,3 +24,20 @@ def _built():
 @pytest.mark.parametrize("threads", ["1", "3"])
 def test_host_code_matches_reference_golden(case, threads):
     check_case(case, run_case(HOSTCHECK, case, extra_args=["-t", threads]))
+
+
+# Many-contig inputs take the host's table-building path (estimator maths on all threads, taker fed in tid order):
+# compare with the oracle on the reference's 54 579-contig fixture.
+@pytest.mark.parametrize("extra", [[], ["--no-zeros"], ["--output-format", "sparse"], ["--min-covered-fraction", "0.3"]],
+                         ids=["dense", "no-zeros", "sparse", "min-covered"])
+@pytest.mark.parametrize("threads", ["1", "5"])
+def test_many_contig_table_path_matches_oracle(extra, threads):
+    from case_runner import DATA, ORACLE_BIN
+    argv = ["contig", "-m", "mean", "trimmed_mean", "covered_fraction", "variance", "rpkm", "tpm", "-b",
+            os.path.join(DATA, "eg2.bam")] + extra
+    a = subprocess.run([HOSTCHECK] + argv + ["-t", threads, "--print-reads-mapped"], capture_output=True, text=True)
+    b = subprocess.run([ORACLE_BIN] + argv + ["--print-reads-mapped"], capture_output=True, text=True)
+    assert a.returncode == b.returncode == 0, a.stderr[-500:]
+    assert a.stdout == b.stdout
+    rm = lambda p: [l for l in p.stderr.splitlines() if l.startswith("#reads_mapped")]
+    assert rm(a) == rm(b)
