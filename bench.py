@@ -143,6 +143,7 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--lib", default=None, help="bind another build of libcoverm_b200.so (kernel A/B experiments)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--contigs", type=int, default=500000)
     ap.add_argument("--reads", type=int, default=10000000)
@@ -154,6 +155,9 @@ def main():
     ap.add_argument("--skip-cpu-baseline", action="store_true")
     ap.add_argument("--workdir", default=os.environ.get("CMB_BENCH_DIR", "/tmp/coverm_b200_bench"))
     args = ap.parse_args()
+    if args.lib:
+        import coverm_b200 as _cb
+        _cb.LIB_PATH = os.path.abspath(args.lib)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

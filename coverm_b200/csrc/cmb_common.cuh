@@ -2,8 +2,11 @@
 #pragma once
 
 
-constexpr uint32_t SPAN = 16;                   // elements per thread span; contig alignment
-constexpr uint32_t K2_THREADS = 512;
+#ifndef CMB_SPAN
+#define CMB_SPAN 32
+#endif
+constexpr uint32_t SPAN = CMB_SPAN;             // elements per thread span; contig alignment (16 or 32)
+constexpr uint32_t K2_THREADS = 8192 / SPAN;
 constexpr uint32_t CHUNK = SPAN * K2_THREADS;   // 8192 elements = 32 KB
 constexpr uint32_t CHUNK_BYTES = CHUNK * 4;
 constexpr uint32_t CHUNK_SPANS = K2_THREADS;    // spans per chunk
@@ -11,7 +14,7 @@ constexpr uint32_t ROW_ELEMS = 32;              // TMA row: 32 x i32 = 128 B
 constexpr uint32_t CHUNK_ROWS = CHUNK / ROW_ELEMS;  // 256
 constexpr uint32_t K2_STAGES = 3;
 constexpr uint32_t K2_WARPS = K2_THREADS / 32;  // 16
-constexpr uint32_t HIST_SLOTS = 16;             // contigs per chunk with a shared-memory histogram (one per K2 warp)
+constexpr uint32_t HIST_SLOTS = 16;             // contigs per chunk with a shared-memory histogram
 constexpr uint32_t HIST_BINS = 128;             // direct-mapped bins per slot: bin = depth % 128, word = tag|count
 constexpr uint32_t HIST_TOTAL = HIST_SLOTS * HIST_BINS;  // 2048
 constexpr uint32_t HIST_CNT_BITS = 14;          // a chunk holds 8192 = 2^13 positions, so a count fits 14 bits

@@ -54,6 +54,10 @@ struct InflateArgs {
   uint32_t* status;
   uint32_t* ticket;
   uint32_t* fail_count;
+  // the kernel runs while the file is still arriving: block b may be read once ready[block_window[b]] != 0
+  // (written by the copy stream after the window's bytes; NULL = everything is resident)
+  const uint32_t* block_window;
+  const uint32_t* ready;
 };
 
 // The compressed stream seen through a 64-bit bit buffer; words come from a per-lane register window.
@@ -69,7 +73,7 @@ struct BitReader {
     ++widx;
     if ((widx & 31) == 0) {
       wcur = wnext;
-      wnext = __ldg(base + widx + 32 + lane);
+      wnext = __ldcg(base + widx + 32 + lane);
     }
     return w;
   }
@@ -77,8 +81,10 @@ struct BitReader {
     const uintptr_t a = (uintptr_t)p;
     base = (const uint32_t*)(a & ~(uintptr_t)127);
     const uint32_t skip = (uint32_t)(a & 127);
-    wcur = __ldg(base + lane);
-    wnext = __ldg(base + 32 + lane);
+    // L2-only loads: the bytes are written by the copy engine while this kernel runs, and the look-ahead of an earlier
+    // block may have touched this line before its window arrived (a stale L1 copy would be read back)
+    wcur = __ldcg(base + lane);
+    wnext = __ldcg(base + 32 + lane);
     widx = skip >> 2;
     const uint32_t drop = (skip & 3) * 8;
     const uint32_t w = next_word(lane);
@@ -218,7 +224,7 @@ __device__ uint32_t inf_block(InfWarpSmem& S, const uint8_t* in, uint32_t in_len
       if ((len ^ nlen) != 0xffff) return 2u /* declined */;
       const uint8_t* src = br.byte_pos();
       if (src + len > in_end || op + len > n_out) return 3u /* declined */;
-      for (uint32_t i = lane; i < len; i += 32) out[op + i] = src[i];
+      for (uint32_t i = lane; i < len; i += 32) out[op + i] = __ldcg(src + i);
       op += len;
       br.init(src + len, lane);
     } else if (btype == 3) {
@@ -352,9 +358,19 @@ __global__ void __launch_bounds__(INF_WARPS * 32, 2) kd_inflate(const InflateArg
     if (lane == 0) b = a.b0 + atomicAdd(a.ticket, 1u);
     b = __shfl_sync(FULL, b, 0);
     if (b >= a.b1) break;
+    bool arrived = true;
+    if (a.ready) {
+      const volatile uint32_t* flag = a.ready + a.block_window[b];
+      uint32_t spins = 0;
+      while (*flag == 0 && spins < (1u << 24)) {  // bounded (~5 s): a copy that never lands must not hang the GPU
+        __nanosleep(256);
+        ++spins;
+      }
+      arrived = __all_sync(FULL, *flag != 0);
+    }
     const uint32_t n_out = a.isize[b];
-    uint32_t st = INF_OK;
-    if (n_out) st = inf_block(S, a.comp + a.coff[b], a.clen[b], a.out + a.uoff[b], n_out, lane, lbase_r, lext_r, dbase_r, dext_r);
+    uint32_t st = arrived ? INF_OK : 31u;
+    if (n_out && arrived) st = inf_block(S, a.comp + a.coff[b], a.clen[b], a.out + a.uoff[b], n_out, lane, lbase_r, lext_r, dbase_r, dext_r);
     __syncwarp();
     if (lane == 0) {
       a.status[b] = st;

@@ -120,8 +120,11 @@ struct cmb_ctx {
     uint64_t *d_coff = nullptr, *d_ustart = nullptr, *d_guess = nullptr, *d_exit = nullptr, *d_rec_base = nullptr, *d_cig_base = nullptr;
     uint32_t *d_clen = nullptr, *d_isize = nullptr, *d_status = nullptr, *d_nrec = nullptr, *d_ncig = nullptr, *d_dirty = nullptr;
     size_t blocks_cap = 0;
-    uint32_t* d_tickets = nullptr;
+    uint32_t* d_tickets = nullptr;  // [0] block ticket, [1 + w] window w has arrived
     size_t tickets_cap = 0;
+    uint32_t* d_block_window = nullptr;
+    size_t block_window_cap = 0;
+    uint32_t* h_ones = nullptr;  // pinned source of the arrival flags
     uint32_t* d_cnt = nullptr;  // [0] inflate failures [1] decode error bits [2] chain changed [4..5] n_primary [6..9] totals
     uint64_t* d_rec_off = nullptr;
     size_t rec_cap = 0;
@@ -465,7 +468,7 @@ void cmb_destroy(cmb_ctx* c) {
     auto& d = c->dec;
     cudaFree(d.d_comp); cudaFree(d.d_inflated); cudaFree(d.d_coff); cudaFree(d.d_ustart); cudaFree(d.d_guess); cudaFree(d.d_exit);
     cudaFree(d.d_rec_base); cudaFree(d.d_cig_base); cudaFree(d.d_clen); cudaFree(d.d_isize); cudaFree(d.d_status); cudaFree(d.d_nrec);
-    cudaFree(d.d_ncig); cudaFree(d.d_dirty); cudaFree(d.d_tickets); cudaFree(d.d_cnt); cudaFree(d.d_rec_off); cudaFree(d.d_tuple_slab);
+    cudaFree(d.d_ncig); cudaFree(d.d_dirty); cudaFree(d.d_tickets); cudaFree(d.d_block_window); if (d.h_ones) cudaFreeHost(d.h_ones); cudaFree(d.d_cnt); cudaFree(d.d_rec_off); cudaFree(d.d_tuple_slab);
     for (auto p : d.pinned) cudaFreeHost(p);
     for (auto st : d.streams) cudaStreamDestroy(st);
     for (auto e : d.slot_events) cudaEventDestroy(e);
@@ -530,7 +533,7 @@ int cmb_set_reference(cmb_ctx* c, uint32_t n_contigs, const uint64_t* contig_len
   c->rec_capacity = (uint32_t)std::min<uint64_t>(0xfffffff0ull, std::max<uint64_t>(1u << 20, c->arena_elems / 8));
   c->ovf_capacity = (uint32_t)std::min<uint64_t>(1u << 26, std::max<uint64_t>(1u << 20, c->arena_elems / 64));
   CU_TRY(c, cudaMalloc(&c->d_rec, 8ull * c->rec_capacity));
-  CU_TRY(c, cudaMalloc(&c->d_warp_table, 8ull * c->n_chunks * K2_WARPS));
+  CU_TRY(c, cudaMalloc(&c->d_warp_table, 8ull * c->n_chunks * HIST_SLOTS));
   CU_TRY(c, cudaMalloc(&c->d_ovf, 16ull * c->ovf_capacity));
   CU_TRY(c, cudaMalloc(&c->d_ovf_head, 4ull * c->n_chunks));
   c->arena_dirty = true;
@@ -816,7 +819,7 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
       byte0 = byte1;
     }
   }
-  if (d.tickets_cap < windows.size() || !d.d_tickets) {
+  if (d.tickets_cap < windows.size() + 1 || !d.d_tickets) {
     cudaFree(d.d_tickets);
     d.d_tickets = nullptr;
     d.tickets_cap = 0;
@@ -824,6 +827,14 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
     CU_TRY(c, cudaMalloc(&d.d_tickets, 4 * want));
     d.tickets_cap = want;
   }
+  if ((rc = dec_grow(c, d.d_block_window, d.block_window_cap, (size_t)nb))) return rc;
+  if (!d.h_ones) {
+    CU_TRY(c, cudaHostAlloc((void**)&d.h_ones, 64, cudaHostAllocDefault));
+    for (int k = 0; k < 16; ++k) d.h_ones[k] = 1;
+  }
+  std::vector<uint32_t> block_window(nb);
+  for (size_t w = 0; w < windows.size(); ++w)
+    for (uint32_t b = windows[w].b0; b < windows[w].b1; ++b) block_window[b] = (uint32_t)w;
   // ---- copy threads, their streams and pinned slots
   cudaPointerAttributes attr{};
   const bool src_pinned = cudaPointerGetAttributes(&attr, in->data) == cudaSuccess && attr.type == cudaMemoryTypeHost;
@@ -852,12 +863,22 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   CU_TRY(c, cudaMemcpyAsync(d.d_isize, in->block_isize, 4ull * nb, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(d.d_ustart, ustart.data(), 8ull * (nb + 1), cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_cnt, 0, 64, c->stream));
-  CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * windows.size(), c->stream));
+  CU_TRY(c, cudaMemcpyAsync(d.d_block_window, block_window.data(), 4ull * nb, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * (windows.size() + 1), c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_inflated + total, 0, DEC_SLACK, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_comp + in->size, 0, DEC_SLACK, c->stream));
   CU_TRY(c, cudaEventRecord(d.ev[1], c->stream));
   CU_TRY(c, cudaFuncSetAttribute(kd_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(d.streams[t], d.ev[1], 0));
+  {  // one persistent launch over every block; its warps wait for their block's window to arrive
+    InflateArgs a{};
+    a.comp = d.d_comp; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
+    a.b0 = 0; a.b1 = nb; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
+    a.block_window = d.d_block_window; a.ready = d.d_tickets + 1;
+    const uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)c->sm_count * 2);
+    kd_inflate<<<grid, INF_WARPS * 32, INF_SMEM_BYTES, c->stream>>>(a);
+    CU_TRY(c, cudaGetLastError());
+  }
   std::atomic<size_t> next_window{0};
   std::atomic<int> first_err{0};
   auto worker = [&](uint32_t t) {
@@ -890,13 +911,7 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
           slot ^= 1;
         }
       }
-      InflateArgs a{};
-      a.comp = d.d_comp; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
-      a.b0 = win.b0; a.b1 = win.b1; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets + w; a.fail_count = d.d_cnt + 0;
-      const uint32_t warps = win.b1 - win.b0;
-      const uint32_t grid = std::min<uint32_t>((warps + INF_WARPS - 1) / INF_WARPS, (uint32_t)c->sm_count * 2);
-      kd_inflate<<<grid, INF_WARPS * 32, INF_SMEM_BYTES, st>>>(a);
-      if (!check(cudaGetLastError())) break;
+      if (!check(cudaMemcpyAsync(d.d_tickets + 1 + w, d.h_ones, 4, cudaMemcpyHostToDevice, st))) break;  // window w has arrived
     }
     check(cudaEventRecord(d.done_events[t], st));
   };
@@ -909,7 +924,12 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   }
   const double copy_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - copy_t0).count();
   (void)copy_wall_ms;
-  out->n_launches = (uint32_t)windows.size();
+  if (first_err.load()) {  // release the warps still waiting for windows that will never arrive
+    cudaMemsetAsync(d.d_tickets + 1, 1, 4 * windows.size(), d.streams[0]);
+    cudaStreamSynchronize(d.streams[0]);
+    cudaStreamSynchronize(c->stream);
+  }
+  out->n_launches = 1;
   out->h2d_bytes = in->size + 24ull * nb + 8;
   if (first_err.load()) return fail(c, CMB_E_CUDA, "cmb_submit_bgzf: copy/inflate stage failed: %s", cudaGetErrorString((cudaError_t)first_err.load()));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(c->stream, d.done_events[t], 0));

@@ -1,11 +1,11 @@
 // K2: segmented prefix sum of the delta arena + every O(L) reduction of EST::add_contig, one pass, HBM-bound.
 //
-// Persistent CTAs (2 per SM, 512 threads).  Each CTA claims 8192-element chunks with an atomic ticket and keeps a
+// Persistent CTAs (2 per SM, 8192/SPAN threads).  Each CTA claims 8192-element chunks with an atomic ticket and keeps a
 // 3-stage ring of 32 KB tiles in flight with TMA (cp.async.bulk.tensor.2d, 128B swizzle, mbarrier complete_tx).  A
-// thread owns one 16-element span (4 x LDS.128, conflict-free through the swizzle); contigs start on span boundaries,
+// thread owns one SPAN-element span (SPAN/4 x LDS.128, conflict-free through the swizzle); contigs start on span boundaries,
 // so a span never straddles two contigs.  Running depth at a span = chunk carry (K1b) + segmented warp/CTA scan of the
 // span totals.  Depth is piecewise constant and deltas are sparse (~1-2 % of positions), so a thread only keeps the
-// span total and a 16-bit mask of its non-zero positions; covered bases, sum of depth and the depth histogram of the
+// span total and a SPAN-bit mask of its non-zero positions; covered bases, sum of depth and the depth histogram of the
 // end-trimmed window are then accumulated per RUN in a short loop over the set bits (the deltas are re-read from the
 // shared-memory tile, which stays resident until the next iteration's barrier).  The histogram lives in shared memory
 // per (contig slot, depth % 128) with the high depth bits as a tag, and is flushed as (depth,count) records while the
@@ -24,7 +24,7 @@ struct K2Args {
   uint2* rec;
   uint32_t rec_capacity;
   uint32_t* rec_count;
-  uint2* warp_table;  // [n_chunks * 16] {offset, count}: records of contig slot w of the chunk
+  uint2* warp_table;  // [n_chunks * HIST_SLOTS] {offset, count}: records of contig slot w of the chunk
   uint4* ovf;         // {contig_local, depth, count, next} — per-chunk linked lists
   uint32_t* ovf_head; // [n_chunks] list heads (OVF_NIL = empty)
   uint32_t ovf_capacity;
@@ -57,35 +57,36 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     }
   };
 
-  // flush one histogram buffer: warp w owns contig slot w (128 bins, 4 per lane) -> (depth,count) records
+  // flush one histogram buffer: a warp takes contig slots warp, warp + K2_WARPS, ... (128 bins, 4 per lane) -> (depth,count) records
   auto flush_hist = [&](uint32_t* hist, uint32_t chunk, uint32_t n_slots) {
-    if (warp >= n_slots) return;  // this chunk has fewer contigs than warps
-    uint32_t word[4], msk[4], total = 0;
-#pragma unroll
-    for (uint32_t k = 0; k < 4; ++k) {
-      word[k] = hist[warp * HIST_BINS + lane + 32 * k];
-      msk[k] = __ballot_sync(FULL, word[k] != 0);
-      total += __popc(msk[k]);
-    }
-    uint32_t base = 0;
-    if (total) {
-      if (lane == 0) base = atomicAdd(a.rec_count, total);
-      base = __shfl_sync(FULL, base, 0);
-      const bool fits = (uint64_t)base + total <= a.rec_capacity;
-      if (!fits && lane == 0) atomicOr(a.error_flags, ERR_CAPACITY);
-      uint32_t before = 0;
+    for (uint32_t sl = warp; sl < HIST_SLOTS && sl < n_slots; sl += K2_WARPS) {
+      uint32_t word[4], msk[4], total = 0;
 #pragma unroll
       for (uint32_t k = 0; k < 4; ++k) {
-        if (word[k]) {
-          const uint32_t depth = ((word[k] >> HIST_CNT_BITS) - 1) * HIST_BINS + lane + 32 * k;
-          if (fits) a.rec[base + before + __popc(msk[k] & ((1u << lane) - 1))] = make_uint2(depth, word[k] & ((1u << HIST_CNT_BITS) - 1));
-          hist[warp * HIST_BINS + lane + 32 * k] = 0;
-        }
-        before += __popc(msk[k]);
+        word[k] = hist[sl * HIST_BINS + lane + 32 * k];
+        msk[k] = __ballot_sync(FULL, word[k] != 0);
+        total += __popc(msk[k]);
       }
-      if (!fits) total = 0;
+      uint32_t base = 0;
+      if (total) {
+        if (lane == 0) base = atomicAdd(a.rec_count, total);
+        base = __shfl_sync(FULL, base, 0);
+        const bool fits = (uint64_t)base + total <= a.rec_capacity;
+        if (!fits && lane == 0) atomicOr(a.error_flags, ERR_CAPACITY);
+        uint32_t before = 0;
+#pragma unroll
+        for (uint32_t k = 0; k < 4; ++k) {
+          if (word[k]) {
+            const uint32_t depth = ((word[k] >> HIST_CNT_BITS) - 1) * HIST_BINS + lane + 32 * k;
+            if (fits) a.rec[base + before + __popc(msk[k] & ((1u << lane) - 1))] = make_uint2(depth, word[k] & ((1u << HIST_CNT_BITS) - 1));
+            hist[sl * HIST_BINS + lane + 32 * k] = 0;
+          }
+          before += __popc(msk[k]);
+        }
+        if (!fits) total = 0;
+      }
+      if (lane == 0) a.warp_table[(uint64_t)chunk * HIST_SLOTS + sl] = make_uint2(base, total);
     }
-    if (lane == 0) a.warp_table[(uint64_t)chunk * K2_WARPS + warp] = make_uint2(base, total);
   };
 
   if (t == 0) {
@@ -99,7 +100,9 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     for (uint32_t s = 0; s < K2_STAGES; ++s) issue(s);
   __syncthreads();
 
-  const uint32_t row = t >> 1, half = t & 1;
+  constexpr uint32_t UNITS = SPAN / 4;                 // 16-byte units per span
+  const uint32_t row = (t * SPAN) / ROW_ELEMS;          // 128-byte tile row holding this thread's span
+  const uint32_t u0 = (t * UNITS) % (ROW_ELEMS / 4);    // its first unit within the row
   const uint32_t E = a.excl;
   uint32_t prev_chunk = 0, prev_slots = 0;
   uint32_t it = 0;
@@ -112,7 +115,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     uint32_t* hist = hist2 + (it & 1) * HIST_TOTAL;
     mbar_wait(smem_u32(full + s), (it / K2_STAGES) & 1);
 
-    // ---- 16 consecutive deltas per thread: 4 x LDS.128 through the 128B swizzle (conflict-free).
+    // ---- SPAN consecutive deltas per thread: LDS.128s through the 128B swizzle (conflict-free).
     //      Only their sum and the mask of non-zero positions stay in registers.
     const uint8_t* rowp = smem + s * CHUNK_BYTES + row * 128;
     const uint32_t span = chunk * CHUNK_SPANS + t;
@@ -121,8 +124,8 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
     {
       int4* g = reinterpret_cast<int4*>(a.arena + (uint64_t)span * SPAN);
 #pragma unroll
-      for (uint32_t j = 0; j < 4; ++j) {
-        const uint32_t unit = (half * 4 + j) ^ (row & 7);
+      for (uint32_t j = 0; j < UNITS; ++j) {
+        const uint32_t unit = (u0 + j) ^ (row & 7);
         const int4 q = *reinterpret_cast<const int4*>(rowp + unit * 16);
         const uint32_t e4 = (q.x != 0 ? 1u : 0u) | (q.y != 0 ? 2u : 0u) | (q.z != 0 ? 4u : 0u) | (q.w != 0 ? 8u : 0u);
         total += (q.x + q.y) + (q.z + q.w);
@@ -261,7 +264,7 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
         const uint32_t j = (uint32_t)__ffs(m) - 1;
         m &= m - 1;
         close_run(depth, from, j);
-        const uint32_t unit = (half * 4 + (j >> 2)) ^ (row & 7);
+        const uint32_t unit = (u0 + (j >> 2)) ^ (row & 7);
         depth += *reinterpret_cast<const int*>(rowp + unit * 16 + (j & 3) * 4);  // the delta at position j
         from = j;
       }

@@ -56,7 +56,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_finalize(const K3Args a) {
       const uint32_t k = k0 + i;
       const uint32_t slot = lc - a.chunk_first[k];
       if (slot >= HIST_SLOTS) continue;
-      const uint2 ent = a.warp_table[(uint64_t)k * K2_WARPS + slot];
+      const uint2 ent = a.warp_table[(uint64_t)k * HIST_SLOTS + slot];
       for (uint32_t r = lane; r < ent.y; r += 32) {
         const uint2 rc = a.rec[ent.x + r];
         fn(rc.x, rc.y);
