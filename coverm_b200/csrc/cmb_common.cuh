@@ -12,9 +12,18 @@ constexpr uint32_t CHUNK_BYTES = CHUNK * 4;
 constexpr uint32_t CHUNK_SPANS = K2_THREADS;    // spans per chunk
 constexpr uint32_t ROW_ELEMS = 32;              // TMA row: 32 x i32 = 128 B
 constexpr uint32_t CHUNK_ROWS = CHUNK / ROW_ELEMS;  // 256
-constexpr uint32_t K2_STAGES = 3;
+#ifndef CMB_K2_STAGES
+#define CMB_K2_STAGES 2
+#endif
+constexpr uint32_t K2_STAGES = CMB_K2_STAGES;
 constexpr uint32_t K2_WARPS = K2_THREADS / 32;  // 16
-constexpr uint32_t HIST_SLOTS = 16;             // contigs per chunk with a shared-memory histogram
+#ifndef CMB_HIST_SLOTS
+#define CMB_HIST_SLOTS 8
+#endif
+#ifndef CMB_K2_MINBLOCKS
+#define CMB_K2_MINBLOCKS 3
+#endif
+constexpr uint32_t HIST_SLOTS = CMB_HIST_SLOTS;             // contigs per chunk with a shared-memory histogram
 constexpr uint32_t HIST_BINS = 128;             // direct-mapped bins per slot: bin = depth % 128, word = tag|count
 constexpr uint32_t HIST_TOTAL = HIST_SLOTS * HIST_BINS;  // 2048
 constexpr uint32_t HIST_CNT_BITS = 14;          // a chunk holds 8192 = 2^13 positions, so a count fits 14 bits
@@ -36,6 +45,9 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
   asm volatile(

@@ -38,7 +38,7 @@ constexpr uint32_t K2_SMEM_BYTES_HIST = K2_SMEM_STAGE_BYTES + K2_SMEM_MISC + 2 *
 constexpr uint32_t K2_SMEM_BYTES_NOHIST = K2_SMEM_STAGE_BYTES + K2_SMEM_MISC;
 
 template <bool HIST, bool CLEAN>
-__global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_constant__ CUtensorMap tmap, const K2Args a) {
+__global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(const __grid_constant__ CUtensorMap tmap, const K2Args a) {
   extern __shared__ __align__(1024) uint8_t smem[];  // stage tiles need the 1024 B swizzle-atom alignment
   uint64_t* full = reinterpret_cast<uint64_t*>(smem + K2_SMEM_STAGE_BYTES);
   uint32_t* s_chunk = reinterpret_cast<uint32_t*>(full + K2_STAGES);
@@ -48,12 +48,16 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
   const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
   auto issue = [&](uint32_t s) {  // thread 0: claim the next chunk and start its TMA load into stage s
+    // The ticket travels with the barrier phase: it is written before the arrive (release) and read by the consumers
+    // after their wait (acquire), so a stage may be refilled for the very next iteration (2-stage rings).
     const uint32_t tk = atomicAdd(a.ticket, 1u);
     s_chunk[s] = tk;
+    const uint32_t bar = smem_u32(full + s);
     if (tk < a.n_chunks) {
-      const uint32_t bar = smem_u32(full + s);
       mbar_arrive_expect_tx(bar, CHUNK_BYTES);
       tma_load_2d(smem_u32(smem + s * CHUNK_BYTES), &tmap, 0, (int32_t)(tk * CHUNK_ROWS), bar);
+    } else {
+      mbar_arrive(bar);  // no more chunks: complete the phase so that the consumers wake up and see the end ticket
     }
   };
 
@@ -109,11 +113,11 @@ __global__ void __launch_bounds__(K2_THREADS, 2) k2_scan_reduce(const __grid_con
 
   for (;; ++it) {
     const uint32_t s = it % K2_STAGES;
-    const uint32_t chunk = s_chunk[s];
+    mbar_wait(smem_u32(full + s), (it / K2_STAGES) & 1);
+    const uint32_t chunk = *(volatile uint32_t*)(s_chunk + s);
     if (chunk >= a.n_chunks) break;
     int2* wagg = wagg2 + (it & 1) * K2_WARPS;
     uint32_t* hist = hist2 + (it & 1) * HIST_TOTAL;
-    mbar_wait(smem_u32(full + s), (it / K2_STAGES) & 1);
 
     // ---- SPAN consecutive deltas per thread: LDS.128s through the 128B swizzle (conflict-free).
     //      Only their sum and the mask of non-zero positions stay in registers.
