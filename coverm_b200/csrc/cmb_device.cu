@@ -2,7 +2,7 @@
 //
 // Data layout in HBM (one cmb_ctx = one GPU = one contig shard):
 //   arena        i32[arena_elems]   all contigs' `ups_and_downs` (contig.rs:144-145) back to back; every contig
-//                                   starts on a 16-element span boundary (SPAN), the arena is a whole number of
+//                                   starts on a 32-element span boundary (SPAN), the arena is a whole number of
 //                                   8192-element chunks (CHUNK).  4 B per reference base.
 //   off_span     u32[n_local+1]     padded contig offsets in span units; len u32[n_local]
 //   chunk_first  u32[n_chunks+1]    contig containing the first span of each chunk
@@ -17,12 +17,14 @@
 //                             +1/-1 delta REDs into the arena (contig.rs:166-202), chunk tail sums.
 //   K1b k1b_chunk_carry       segmented scan of the per-chunk tail sums -> carry_in (so K2 needs no look-back).
 //   K2  k2_scan_reduce        persistent CTAs, TMA (cp.async.bulk.tensor, 128B swizzle) + mbarrier ring of 32 KB
-//                             chunks, blocked 16-element spans per thread, warp-shuffle segmented scan, then every
+//                             chunks, blocked 32-element spans per thread, warp-shuffle segmented scan, then every
 //                             O(L) reduction of EST:366-502 in one pass: sum/covered over the end-trimmed window,
 //                             covered over the full contig, window depth histogram into a shared-memory table that
 //                             is flushed as (depth,count) records; optionally re-zeroes the arena as it goes.
 //   K3  k3_finalize           per contig: merge the records, trimmed-mean walk (EST:598-642) and the variance sums
 //                             (EST:790-805) in integers; optional CSR histogram output.
+//   KD* kd_inflate ...        device-side BAM decode behind cmb_submit_bgzf (cmb_decode.cuh): BGZF inflate, record chain,
+//                             tuple extraction -- the compressed file crosses PCIe instead of tuples.
 #include <cuda.h>
 #include <cuda_runtime.h>
 
