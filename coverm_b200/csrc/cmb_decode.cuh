@@ -6,7 +6,8 @@
 //                    flow), which turns the lanes into resources: the compressed bytes are held as a 2 x 128-byte
 //                    register window fetched with coalesced loads and read with shuffles; length/distance base tables
 //                    live one entry per lane; LZ77 matches are copied by all lanes; Huffman tables (10-bit root + 5-bit
-//                    subtables, u16 entries) are built cooperatively in shared memory.
+//                    subtables, u16 entries) are built cooperatively in shared memory.  The block's CRC-32 is then
+//                    checked against the BGZF footer (per-lane slices combined in GF(2)).
 //   KD2 kd_guess     one warp per block: the first offset >= the block start from which a chain of plausible record
 //                    headers runs (records straddle blocks freely).
 //   KD3 kd_walk      one thread per block: follow block_size from the guess to the block end -> exit offset, counts.
@@ -35,7 +36,7 @@ struct InfWarpSmem {
   uint32_t overflow;
   uint32_t pad[3];
 };
-constexpr uint32_t INF_SMEM_BYTES = INF_WARPS * sizeof(InfWarpSmem);
+constexpr uint32_t INF_SMEM_BYTES = INF_WARPS * sizeof(InfWarpSmem) + 4 * 256 * 4 /* CRC-32 slicing tables */;
 
 __constant__ uint16_t c_len_base[32] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258, 0, 0, 0};
 __constant__ uint8_t c_len_extra[32] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0, 0, 0, 0};
@@ -348,10 +349,69 @@ __device__ uint32_t inf_block(InfWarpSmem& S, const uint8_t* in, uint32_t in_len
   return INF_OK;
 }
 
+// ---- CRC-32 (ISO-HDLC, the gzip/BGZF checksum; reflected polynomial 0xEDB88320) of a block's output, by the whole warp:
+// every lane checksums a 2 KB slice with slicing-by-4 tables, then the slices are combined through the linearity of the
+// CRC: crc(A||B) = crc(A) * x^(8|B|) mod P  xor  crc(B)  (polynomial arithmetic over GF(2), bit 31 = x^0).
+constexpr uint32_t CRC_POLY = 0xedb88320u;
+constexpr uint32_t CRC_SLICE = 2048;
+constexpr uint32_t INF_CRC_TABLE_BYTES = 4 * 256 * 4;
+
+__device__ __forceinline__ uint32_t gf2_mulmod(uint32_t a, uint32_t b) {  // a(x) * b(x) mod P(x)
+  uint32_t p = 0;
+  for (uint32_t m = 1u << 31; m; m >>= 1) {
+    if (a & m) p ^= b;
+    b = (b & 1) ? (b >> 1) ^ CRC_POLY : b >> 1;
+  }
+  return p;
+}
+__device__ uint32_t gf2_x_pow_8n(uint32_t n_bytes) {  // x^(8 n) mod P by square and multiply
+  uint32_t sq = 0x00800000u;  // x^8: x^0 is bit 31, x^k is bit 31-k
+  uint32_t r = 1u << 31;
+  while (n_bytes) {
+    if (n_bytes & 1) r = gf2_mulmod(sq, r);
+    sq = gf2_mulmod(sq, sq);
+    n_bytes >>= 1;
+  }
+  return r;
+}
+__device__ uint32_t warp_crc32(const uint8_t* data, uint32_t n, const uint32_t* T, uint32_t lane) {
+  const uint32_t b0 = min(n, lane * CRC_SLICE), b1 = min(n, (lane + 1) * CRC_SLICE);
+  uint32_t c = 0;
+  if (b1 > b0) {
+    const uint8_t* p = data + b0;
+    const uint8_t* e = data + b1;
+    c = 0xffffffffu;
+    while (p < e && ((uintptr_t)p & 3)) c = T[(c ^ __ldcg(p++)) & 0xff] ^ (c >> 8);
+    for (; p + 4 <= e; p += 4) {
+      c ^= __ldcg(reinterpret_cast<const uint32_t*>(p));
+      c = T[768 + (c & 0xff)] ^ T[512 + ((c >> 8) & 0xff)] ^ T[256 + ((c >> 16) & 0xff)] ^ T[c >> 24];
+    }
+    while (p < e) c = T[(c ^ __ldcg(p++)) & 0xff] ^ (c >> 8);
+    c = ~c;
+    c = gf2_mulmod(gf2_x_pow_8n(n - b1), c);
+  }
+  return __reduce_xor_sync(FULL, c);
+}
+
 __global__ void __launch_bounds__(INF_WARPS * 32, 2) kd_inflate(const InflateArgs a) {
   extern __shared__ __align__(16) uint8_t inf_smem[];
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   InfWarpSmem& S = reinterpret_cast<InfWarpSmem*>(inf_smem)[warp];
+  uint32_t* crcT = reinterpret_cast<uint32_t*>(inf_smem + INF_WARPS * sizeof(InfWarpSmem));
+  if (threadIdx.x < 256) {
+    uint32_t c = threadIdx.x;
+    for (int k = 0; k < 8; ++k) c = (c & 1) ? (c >> 1) ^ CRC_POLY : c >> 1;
+    crcT[threadIdx.x] = c;
+  }
+  __syncthreads();
+  if (threadIdx.x < 256) {
+    uint32_t c = crcT[threadIdx.x];
+    for (int k = 1; k < 4; ++k) {
+      c = crcT[c & 0xff] ^ (c >> 8);
+      crcT[k * 256 + threadIdx.x] = c;
+    }
+  }
+  __syncthreads();
   const uint32_t lbase_r = c_len_base[lane], lext_r = c_len_extra[lane], dbase_r = c_dist_base[lane], dext_r = c_dist_extra[lane];
   for (;;) {
     uint32_t b = 0;
@@ -370,7 +430,17 @@ __global__ void __launch_bounds__(INF_WARPS * 32, 2) kd_inflate(const InflateArg
     }
     const uint32_t n_out = a.isize[b];
     uint32_t st = arrived ? INF_OK : 31u;
-    if (n_out && arrived) st = inf_block(S, a.comp + a.coff[b], a.clen[b], a.out + a.uoff[b], n_out, lane, lbase_r, lext_r, dbase_r, dext_r);
+    if (n_out && arrived) {
+      const uint8_t* in = a.comp + a.coff[b];
+      const uint32_t in_len = a.clen[b];
+      st = inf_block(S, in, in_len, a.out + a.uoff[b], n_out, lane, lbase_r, lext_r, dbase_r, dext_r);
+      __syncwarp();
+      if (st == INF_OK) {  // htslib verifies the block's CRC32 (bgzf.c); so do we, from the footer that follows the payload
+        const uint8_t* f = in + in_len;
+        const uint32_t want = (uint32_t)__ldcg(f) | ((uint32_t)__ldcg(f + 1) << 8) | ((uint32_t)__ldcg(f + 2) << 16) | ((uint32_t)__ldcg(f + 3) << 24);
+        if (warp_crc32(a.out + a.uoff[b], n_out, crcT, lane) != want) st = 30u;
+      }
+    }
     __syncwarp();
     if (lane == 0) {
       a.status[b] = st;

@@ -232,6 +232,9 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
             items_finished.fetch_add(1);
           }
           ++h;
+          // bytes left over after the last item are a record cut short: htslib's bam_read1 fails there and the reference
+          // panics on the Err (contig.rs:113-115)
+          if (h == n_items && !carry.empty()) throw Panic("Error reading BAM record: truncated");
           chain_head.store(h, std::memory_order_release);
         }
       } catch (...) {
