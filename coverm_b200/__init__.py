@@ -170,18 +170,33 @@ def load_library(path=None):
 
 
 class RunResult:
-    """status / stdout / stderr of one in-process `coverm` run.  ``out_bytes`` is the table exactly as the C ABI returned
-    it; ``out`` decodes it to str on first use."""
+    """status / stdout / stderr of one in-process `coverm` run.  The table text stays in the buffer the C ABI returned
+    (``out_len`` bytes, freed with this object); ``out_bytes`` / ``out`` copy / decode it on first use."""
 
-    def __init__(self, status, out_bytes, err, samples):
-        self.status, self.out_bytes, self.err, self.samples = status, out_bytes, err, samples
-        self._out = None
+    def __init__(self, lib, res, err, samples):
+        self._lib, self._res = lib, res
+        self.status, self.out_len, self.err, self.samples = res.status, res.out_len, err, samples
+        self._bytes = self._out = None
+
+    @property
+    def out_bytes(self):
+        if self._bytes is None:
+            self._bytes = C.string_at(self._res.out, self._res.out_len) if self._res.out else b""
+        return self._bytes
 
     @property
     def out(self):
         if self._out is None:
             self._out = self.out_bytes.decode()
         return self._out
+
+    def __del__(self):
+        try:
+            if self._res is not None:
+                self._lib.cmbh_free_result(C.byref(self._res))
+                self._res = None
+        except Exception:
+            pass
 
 
 class Session:
@@ -223,15 +238,12 @@ class Session:
         rc = lib.cmbh_run(self._h, len(argv), args, mem, n_mem, C.byref(res))
         if rc != 0:
             raise CmbError(f"cmbh_run failed with {rc}")
-        out = C.string_at(res.out, res.out_len) if res.out else b""
         err = C.string_at(res.err, res.err_len).decode() if res.err else ""
         samples = []
         for i in range(res.n_samples):
             s = res.samples[i]
             samples.append({f[0]: getattr(s, f[0]) for f in SampleInfo._fields_})
-        status = res.status
-        lib.cmbh_free_result(C.byref(res))
-        return RunResult(status, out, err, samples)
+        return RunResult(lib, res, err, samples)
 
     def close(self):
         if self._h:

@@ -80,7 +80,7 @@ inline const cmb_hist_pair* no_pairs() {
 inline ContigObservation observe(const SampleResult& r, uint32_t tid, CountMode mode, bool csr) {
   const cmb_contig_stats& s = r.rows[tid];
   ContigObservation ob;
-  ob.len = r.header.lens[tid];
+  ob.len = r.header().lens[tid];
   ob.stats = &s;
   ob.total_mismatches = s.sum_edit - s.sum_indel;  // unchecked u64 subtraction (contig.rs:59)
   switch (mode) {
@@ -128,7 +128,7 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
     const SampleResult r = run_sample(io, in);
     coverage_taker.start_stoit(r.stoit_name);
     uint64_t num_mapped_reads_total = 0;
-    const uint32_t n = (uint32_t)r.header.names.size();
+    const uint32_t n = (uint32_t)r.header().names.size();
     std::vector<float> coverages(coverage_estimators.size());
     const std::vector<uint64_t> contig_mode_unobserved{0};  // calculate_coverage(&[0]), contig.rs:65
     bool any_pileup = false;
@@ -167,12 +167,12 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
       for (uint32_t tid = 0; tid < n; ++tid) {
         if (state[tid] == 0) {
           if (print_zero_coverage_contigs) {
-            coverage_taker.start_entry(tid, r.header.names[tid]);
-            for (auto& e : coverage_estimators) e.print_zero_coverage(coverage_taker, r.header.lens[tid]);
+            coverage_taker.start_entry(tid, r.header().names[tid]);
+            for (auto& e : coverage_estimators) e.print_zero_coverage(coverage_taker, r.header().lens[tid]);
             coverage_taker.finish_entry();
           }
         } else if (print_zero_coverage_contigs || state[tid] == 2) {
-          coverage_taker.start_entry(tid, r.header.names[tid]);
+          coverage_taker.start_entry(tid, r.header().names[tid]);
           for (size_t k = 0; k < K; ++k) coverage_estimators[k].print_coverage(vals[(size_t)tid * K + k], coverage_taker);
           coverage_taker.finish_entry();
         }
@@ -183,8 +183,8 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
     for (uint32_t tid = 0; tid < n; ++tid) {
       if (r.rows[tid].n_records == 0) {  // never seen: print_previous_zero_coverage_contigs (:255-277)
         if (print_zero_coverage_contigs) {
-          coverage_taker.start_entry(tid, r.header.names[tid]);
-          for (auto& e : coverage_estimators) e.print_zero_coverage(coverage_taker, r.header.lens[tid]);
+          coverage_taker.start_entry(tid, r.header().names[tid]);
+          for (auto& e : coverage_estimators) e.print_zero_coverage(coverage_taker, r.header().lens[tid]);
           coverage_taker.finish_entry();
         }
         continue;
@@ -198,7 +198,7 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
       }
       if (has_nonzero) num_mapped_reads_total += ob.num_mapped_reads;
       if (print_zero_coverage_contigs || has_nonzero) {
-        coverage_taker.start_entry(tid, r.header.names[tid]);
+        coverage_taker.start_entry(tid, r.header().names[tid]);
         for (size_t k = 0; k < coverage_estimators.size(); ++k) coverage_estimators[k].print_coverage(coverages[k], coverage_taker);
         coverage_taker.finish_entry();
       }
@@ -219,12 +219,12 @@ inline std::vector<ReadsMapped> mosdepth_genome_coverage_with_contig_names(
   for (const InputSpec& in : bam_readers) {
     const SampleResult r = run_sample(io, in);
     coverage_taker.start_stoit(r.stoit_name);
-    const uint32_t n = (uint32_t)r.header.names.size();
+    const uint32_t n = (uint32_t)r.header().names.size();
     std::vector<int64_t> genome_of(n, -1);
     std::vector<std::vector<uint32_t>> refs_of(n_genomes);
     uint32_t in_genomes = 0;
     for (uint32_t tid = 0; tid < n; ++tid) {
-      auto it = contigs_and_genomes.contig_to_genome.find(r.header.names[tid]);
+      auto it = contigs_and_genomes.contig_to_genome.find(r.header().names[tid]);
       if (it == contigs_and_genomes.contig_to_genome.end()) continue;
       genome_of[tid] = (int64_t)it->second;
       refs_of[it->second].push_back(tid);
@@ -254,8 +254,8 @@ inline std::vector<ReadsMapped> mosdepth_genome_coverage_with_contig_names(
         std::vector<uint64_t> unobserved;
         uint64_t genome_len = 0;
         for (uint32_t tid : refs_of[g]) {
-          genome_len += r.header.lens[tid];
-          if (r.rows[tid].n_records == 0) unobserved.push_back(r.header.lens[tid]);
+          genome_len += r.header().lens[tid];
+          if (r.rows[tid].n_records == 0) unobserved.push_back(r.header().lens[tid]);
         }
         std::vector<float> coverages;
         bool any_nonzero = false;
@@ -367,7 +367,7 @@ inline std::vector<ReadsMapped> mosdepth_genome_coverage(const std::vector<Input
   for (const InputSpec& in : bam_readers) {
     const SampleResult r = run_sample(io, in);
     coverage_taker.start_stoit(r.stoit_name);
-    const Header& h = r.header;
+    const Header& h = r.header();
     const Walk walk{h, split_char, single_genome};
     const uint32_t n = (uint32_t)h.names.size();
 

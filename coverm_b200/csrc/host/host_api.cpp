@@ -12,6 +12,48 @@ struct cmbh_session {
 
 namespace {
 std::string g_err;
+// An ostream buffer that grows a malloc'd array and hands it over (the table text reaches the caller without a copy).
+class MallocBuf : public std::streambuf {
+ public:
+  ~MallocBuf() override { free(p_); }
+  char* release(size_t* len) {
+    if (!p_) reserve(1);
+    p_[n_] = 0;
+    *len = n_;
+    char* r = p_;
+    p_ = nullptr;
+    n_ = cap_ = 0;
+    return r;
+  }
+
+ protected:
+  std::streamsize xsputn(const char* s, std::streamsize n) override {
+    reserve(n_ + (size_t)n + 1);
+    memcpy(p_ + n_, s, (size_t)n);
+    n_ += (size_t)n;
+    return n;
+  }
+  int_type overflow(int_type ch) override {
+    if (ch != traits_type::eof()) {
+      reserve(n_ + 2);
+      p_[n_++] = (char)ch;
+    }
+    return ch;
+  }
+
+ private:
+  void reserve(size_t need) {
+    if (need <= cap_) return;
+    size_t ncap = cap_ ? cap_ : (1u << 16);
+    while (ncap < need) ncap *= 2;
+    char* np = (char*)realloc(p_, ncap);
+    if (!np) throw std::bad_alloc();
+    p_ = np;
+    cap_ = ncap;
+  }
+  char* p_ = nullptr;
+  size_t n_ = 0, cap_ = 0;
+};
 char* dup_text(const std::string& s) {
   char* p = (char*)malloc(s.size() + 1);
   if (p) {
@@ -60,12 +102,14 @@ int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_
     in.size = mem[i].size;
     inputs.push_back(in);
   }
-  std::ostringstream out, err;
+  MallocBuf out_buf;
+  std::ostream out(&out_buf);
+  std::ostringstream err;
   const CliResult r = run_cli(args, inputs, out, err, s ? s->dev.get() : nullptr);
+  out.flush();
   res->status = r.status;
-  const std::string so = out.str(), se = err.str();
-  res->out = dup_text(so);
-  res->out_len = so.size();
+  const std::string se = err.str();
+  res->out = out_buf.release(&res->out_len);
   res->err = dup_text(se);
   res->err_len = se.size();
   res->n_samples = (uint32_t)std::min<size_t>(CMBH_MAX_SAMPLES, r.timings.size());

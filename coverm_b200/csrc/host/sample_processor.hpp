@@ -33,7 +33,8 @@ struct SampleTiming {
 
 struct SampleResult {
   std::string stoit_name;
-  Header header;
+  std::shared_ptr<Header> hdr = std::make_shared<Header>();  // shared with the session's header cache
+  const Header& header() const { return *hdr; }
   const cmb_contig_stats* rows = nullptr;  // n_ref rows in the session's page-locked buffer; valid until the next process()
   std::vector<cmb_hist_pair> pairs;
   uint64_t num_detected_primary_alignments = 0;  // bam_generator.rs:113-119 / filter.rs:94-96,129-131
@@ -205,7 +206,7 @@ class DeviceSession {
     const uint8_t* p = bytes.data();
     size_t n = bytes.size();
     if (!(n >= 2 && p[0] == 0x1f && p[1] == 0x8b) && SamToBam::looks_like_sam(p, n)) {
-      SamToBam::convert(p, n, res.header, sam_as_bam);
+      SamToBam::convert(p, n, *res.hdr, sam_as_bam);
       p = sam_as_bam.data();
       n = sam_as_bam.size();
     }
@@ -228,31 +229,44 @@ class DeviceSession {
       }
       return true;
     };
-    // ---- header (SAMv1 §4.2)
+    // ---- header (SAMv1 §4.2).  Samples mapped to the same reference carry byte-identical headers up to the first record:
+    //      the parsed copy of the previous sample is reused then (500 000 names are not rebuilt per sample).
+    uint64_t records_at = 0;
+    uint32_t n_ref = 0;
     if (!need(12) || memcmp(buf.data() + begin, "BAM\1", 4) != 0) throw Panic("Error reading BAM header: not a BAM/SAM file: " + in.path);
     const uint32_t l_text = rd_u32(buf.data() + begin + 4);
     if (!need(12 + (size_t)l_text)) throw Panic("Error reading BAM header: truncated");
-    const uint32_t n_ref = rd_u32(buf.data() + begin + 8 + l_text);
-    size_t o = 12 + (size_t)l_text;
-    res.header.names.reserve(n_ref);
-    res.header.lens.reserve(n_ref);
-    for (uint32_t i = 0; i < n_ref; ++i) {
-      if (!need(o + 4)) throw Panic("Error reading BAM header: truncated");
-      const uint32_t l_name = rd_u32(buf.data() + begin + o);
-      if (!need(o + 8 + l_name)) throw Panic("Error reading BAM header: truncated");
-      res.header.names.emplace_back((const char*)buf.data() + begin + o + 4, l_name ? l_name - 1 : 0);
-      res.header.lens.push_back(rd_u32(buf.data() + begin + o + 4 + l_name));
-      o += 8 + l_name;
+    const size_t refs_at = 8 + (size_t)l_text;  // the n_ref field; the @-lines before it (e.g. @PG) may differ between samples
+    if (hdr_cache_ && hdr_raw_.size() >= 4 && need(refs_at + hdr_raw_.size()) &&
+        memcmp(buf.data() + begin + refs_at, hdr_raw_.data(), hdr_raw_.size()) == 0) {
+      res.hdr = hdr_cache_;
+      n_ref = (uint32_t)res.hdr->names.size();
+      records_at = refs_at + hdr_raw_.size();
+    } else {
+      n_ref = rd_u32(buf.data() + begin + refs_at);
+      size_t o = refs_at + 4;
+      res.hdr->names.reserve(n_ref);
+      res.hdr->lens.reserve(n_ref);
+      for (uint32_t i = 0; i < n_ref; ++i) {
+        if (!need(o + 4)) throw Panic("Error reading BAM header: truncated");
+        const uint32_t l_name = rd_u32(buf.data() + begin + o);
+        if (!need(o + 8 + l_name)) throw Panic("Error reading BAM header: truncated");
+        res.hdr->names.emplace_back((const char*)buf.data() + begin + o + 4, l_name ? l_name - 1 : 0);
+        res.hdr->lens.push_back(rd_u32(buf.data() + begin + o + 4 + l_name));
+        o += 8 + l_name;
+      }
+      records_at = o;  // uncompressed offset of the first record (nothing has been discarded yet)
+      hdr_raw_.assign(buf.data() + begin + refs_at, buf.data() + begin + o);
+      hdr_cache_ = res.hdr;
     }
-    const uint64_t records_at = o;  // uncompressed offset of the first record (nothing has been discarded yet)
-    begin += o;
+    begin += records_at;
 
     // ---- device reference + params
     const uint32_t sb = std::min<uint32_t>(shard_begin_, n_ref), se = std::min<uint32_t>(shard_end_, n_ref);
-    if (res.header.lens != ref_lens_) {
-      rc = cmb_set_reference(ctx_, n_ref, res.header.lens.data(), sb, se);
+    if (res.hdr->lens != ref_lens_) {
+      rc = cmb_set_reference(ctx_, n_ref, res.hdr->lens.data(), sb, se);
       if (rc) throw_device_error(ctx_, rc);
-      ref_lens_ = res.header.lens;
+      ref_lens_ = res.hdr->lens;
     }
     rc = cmb_begin_sample(ctx_);
     if (rc) throw_device_error(ctx_, rc);
@@ -477,6 +491,8 @@ class DeviceSession {
   }
 
  private:
+  std::shared_ptr<Header> hdr_cache_;  // parsed reference list of the previous sample and its raw bytes (n_ref .. first record)
+  std::vector<uint8_t> hdr_raw_;
   cmb_contig_stats* rows_buf_ = nullptr;
   size_t rows_cap_ = 0;
   ThreadPool pool_;
