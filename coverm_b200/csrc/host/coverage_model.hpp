@@ -18,6 +18,13 @@
 
 namespace cmbh {
 
+// Stage timings on stderr when CMB_HOST_STATS is set (profiling aid).
+inline double host_now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
+inline void host_stat(const char* what, double seconds) {
+  static const bool on = getenv("CMB_HOST_STATS") != nullptr;
+  if (on) fprintf(stderr, "#host_stat\t%s\t%.4f\n", what, seconds);
+}
+
 template <class F>
 inline std::string rust_display(F v) {  // Rust `{}` for f32/f64: shortest round-trip digits, fixed notation
   if (std::isnan(v)) return "NaN";
@@ -54,6 +61,29 @@ class CoverageTaker {  // coverage_takers.rs:29-38 (trait) over the three Covera
   size_t num_coverages = 0;
   std::vector<std::string> stoit_names;
   std::vector<std::optional<std::string>> entry_names;
+  // Contig mode with many entries: the names are the BAM header's, shared instead of copied entry by entry.  While set,
+  // entry_names stays empty; entry_name() serves both representations.
+  std::shared_ptr<const std::vector<std::string>> shared_names;
+  const std::string* entry_name(size_t idx) const {
+    if (shared_names) return idx < shared_names->size() ? &(*shared_names)[idx] : nullptr;
+    return idx < entry_names.size() && entry_names[idx] ? &*entry_names[idx] : nullptr;
+  }
+  // Adopt `names` for every entry index (true), or report that they conflict with what is already recorded (false: the
+  // caller then goes through start_entry(), which raises the reference's error at the first differing entry).
+  bool try_share_names(const std::shared_ptr<const std::vector<std::string>>& names) {
+    if (kind != Kind::CachedSingleFloat) return false;
+    if (!shared_names && entry_names.empty()) {
+      shared_names = names;
+      return true;
+    }
+    return shared_names && (shared_names == names || *shared_names == *names);
+  }
+  void start_entry_shared(size_t order_id) { cur_entry_index_ = order_id; }
+  void unshare_names() {  // back to per-entry names (a later input has entries the shared list lacks)
+    if (!shared_names) return;
+    entry_names.assign(shared_names->begin(), shared_names->end());
+    shared_names.reset();
+  }
   struct Entry { size_t entry_index; float coverage; };
   std::vector<std::vector<Entry>> coverages;
 
@@ -64,7 +94,7 @@ class CoverageTaker {  // coverage_takers.rs:29-38 (trait) over the three Covera
   // Capacity hint (cached taker): n_entries entries of k coverages are about to be added to the current stoit.
   void reserve_entries(size_t n_entries, size_t k) {
     if (kind != Kind::CachedSingleFloat) return;
-    if (entry_names.size() < n_entries) entry_names.resize(n_entries);
+    if (!shared_names && entry_names.size() < n_entries) entry_names.resize(n_entries);
     coverages[cur_stoit_index_].reserve(coverages[cur_stoit_index_].size() + n_entries * k);
   }
   void start_stoit(const std::string& name) {
@@ -82,6 +112,17 @@ class CoverageTaker {  // coverage_takers.rs:29-38 (trait) over the three Covera
     } else if (kind == Kind::PileupStreaming) {
       cur_entry_ = name;
     } else {
+      if (shared_names) {
+        if (order_id < shared_names->size() && (*shared_names)[order_id] == name) {
+          cur_entry_index_ = order_id;
+          return;
+        }
+        if (order_id >= shared_names->size()) unshare_names();
+        else
+          throw ExitError(1, "Found a difference amongst the reference sets used for mapping. For this (non-streaming) usage of "
+                             "CoverM, all BAM files must have the same set of reference sequences. Previous entry was " +
+                                 (*shared_names)[order_id] + ", new is " + name);
+      }
       if (order_id >= entry_names.size()) entry_names.resize(order_id + 1);
       if (!entry_names[order_id]) entry_names[order_id] = name;
       if (*entry_names[order_id] != name)
@@ -503,7 +544,7 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
     for (size_t e = 0; e < by_stoit[0].size(); ++e) {
       float total_depth = 0.0f;
       for (auto& st : by_stoit) total_depth += st[e].coverages[1];
-      os << *taker.entry_names[e] << '\t' << rust_display(by_stoit[0][e].coverages[0]) << '\t'
+      os << *taker.entry_name(e) << '\t' << rust_display(by_stoit[0][e].coverages[0]) << '\t'
          << rust_display(std::round((double)total_depth * 10000.0 / (double)taker.coverages.size()) / 10000.0);
       for (auto& st : by_stoit)
         os << '\t' << rust_display(std::round((double)st[e].coverages[1] * 10000.0) / 10000.0) << '\t'
@@ -523,15 +564,25 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
       t.reserve(BLOCK * 48);
       for (size_t i = b * BLOCK; i < std::min(n, (b + 1) * BLOCK); ++i) row(i, t);
     };
+    const double t0 = host_now();
     if (pool && n_blocks > 1) pool->parallel_for(n_blocks, do_block);
     else for (size_t b = 0; b < n_blocks; ++b) do_block(b, 0);
+    const double t1 = host_now();
     for (auto& t : text) os.write(t.data(), (std::streamsize)t.size());
+    host_stat("write_rows.format", t1 - t0);
+    host_stat("write_rows.concat", host_now() - t1);
   }
 
   void sparse(const CoverageTaker& taker, std::ostream& os, const std::vector<ReadsMapped>& rm,
               const std::vector<size_t>& norm, std::optional<size_t> rpkm, std::optional<size_t> tpm) {  // :155-356
     const size_t nc = taker.num_coverages;
     size_t extra_cols = 0;
+    if (taker.shared_names) {  // the lowest entry index any stoit recorded
+      std::optional<size_t> first;
+      for (auto& c : taker.coverages)
+        if (!c.empty() && (!first || c[0].entry_index < *first)) first = c[0].entry_index;
+      if (first && taker.entry_name(*first)) extra_cols = tabs(*taker.entry_name(*first));
+    }
     for (auto& n : taker.entry_names)
       if (n) { extra_cols = tabs(*n); break; }
     const auto cells = taker.cells_by_stoit();
@@ -562,13 +613,13 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
         os << '\n';
       }
       for (auto& r : rows)
-        if (!taker.entry_names[r.entry_index]) throw ExitError(1, "Didn't find entry name string as expected");
+        if (!taker.entry_name(r.entry_index)) throw ExitError(1, "Didn't find entry name string as expected");
       const uint64_t n_mapped = rm.empty() ? 0 : rm[stoit].num_mapped_reads;
       write_rows(os, rows.size(), [&](size_t i, std::string& t) {
         const auto& r = rows[i];
         t += name;
         t += '\t';
-        t += strip_cr(*taker.entry_names[r.entry_index]);
+        t += strip_cr(*taker.entry_name(r.entry_index));
         for (size_t c = 0; c < nc; ++c) {
           t += '\t';
           const float cov = r.at(c);
@@ -598,7 +649,9 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
       for (size_t s = 0; s < ns; ++s) unmapped_columns(os, norm, nc, [&](size_t) { return rust_display(100.0f * (1.0f - mult[s])); });
       os << '\n';
     }
+    const double t_cells0 = host_now();
     const auto cells = taker.cells_by_stoit();
+    host_stat("dense.cells_by_stoit", host_now() - t_cells0);
     std::vector<std::vector<float>> totals(ns, std::vector<float>(nc, 0.0f));
     for (size_t s = 0; s < cells.size(); ++s) {
       auto accumulate = [&](size_t c) {  // first value seeds the total, later ones are added (:457-477)
@@ -617,7 +670,7 @@ class CoveragePrinter {  // coverage_printer.rs:9-17
     while (n_filled < cells.size() && !cells[n_filled].empty()) ++n_filled;
     if (n_filled == 0) throw Panic("index out of bounds: the len is 0 but the index is 0");
     write_rows(os, cells[0].size(), [&](size_t e, std::string& t) {
-      t += strip_cr(*taker.entry_names[cells[0][e].entry_index]);
+      t += strip_cr(*taker.entry_name(cells[0][e].entry_index));
       for (size_t s = 0; s < n_filled; ++s) {
         const auto& r = cells[s][e];
         const uint64_t n_mapped = rm.empty() ? 0 : rm[s].num_mapped_reads;

@@ -142,6 +142,7 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
       ThreadPool& pool = io.session->pool();
       const size_t n_tasks = std::min<size_t>((size_t)pool.size() * 4, (n + 4095) / 4096);
       std::vector<uint64_t> task_mapped(n_tasks, 0);
+      const double t_table0 = host_now();
       pool.parallel_for(n_tasks, [&](size_t task, int) {
         std::vector<CoverageEstimator> est = coverage_estimators;
         const uint32_t t0 = (uint32_t)((uint64_t)n * task / n_tasks), t1 = (uint32_t)((uint64_t)n * (task + 1) / n_tasks);
@@ -163,20 +164,28 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
         task_mapped[task] = mapped;
       });
       for (uint64_t m : task_mapped) num_mapped_reads_total += m;
+      const double t_feed0 = host_now();
+      host_stat("contig.estimator_table", t_feed0 - t_table0);
+      const bool shared = coverage_taker.try_share_names(std::shared_ptr<const std::vector<std::string>>(r.hdr, &r.hdr->names));
       coverage_taker.reserve_entries(n, K);
+      auto start_entry = [&](uint32_t tid) {
+        if (shared) coverage_taker.start_entry_shared(tid);
+        else coverage_taker.start_entry(tid, r.header().names[tid]);
+      };
       for (uint32_t tid = 0; tid < n; ++tid) {
         if (state[tid] == 0) {
           if (print_zero_coverage_contigs) {
-            coverage_taker.start_entry(tid, r.header().names[tid]);
+            start_entry(tid);
             for (auto& e : coverage_estimators) e.print_zero_coverage(coverage_taker, r.header().lens[tid]);
             coverage_taker.finish_entry();
           }
         } else if (print_zero_coverage_contigs || state[tid] == 2) {
-          coverage_taker.start_entry(tid, r.header().names[tid]);
+          start_entry(tid);
           for (size_t k = 0; k < K; ++k) coverage_estimators[k].print_coverage(vals[(size_t)tid * K + k], coverage_taker);
           coverage_taker.finish_entry();
         }
       }
+      host_stat("contig.taker_feed", host_now() - t_feed0);
       reads_mapped_vector.push_back({num_mapped_reads_total, r.num_detected_primary_alignments});
       continue;
     }

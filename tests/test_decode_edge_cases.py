@@ -96,3 +96,45 @@ def test_device_decoder_edge_cases(files, name):
         st = [l for l in g.stderr.splitlines() if l.startswith("#decode_") or l.startswith("#device_decode")]
         assert any(l.startswith("#decode_verify\t0 of ") for l in st), st  # device-inflated bytes == zlib's, block by block
     _same(_run(coverm_b200.COVERM_BIN, files[name], env={"CMB_HOST_DECODE": "1"}), o, name)
+
+
+# ---- many-contig inputs share the header's names with the cached taker; a second sample with a different reference must
+#      still fail exactly like the reference ("Found a difference amongst the reference sets", coverage_takers.rs:138-149)
+@pytest.fixture(scope="module")
+def many_contig_pair(tmp_path_factory):
+    d = tmp_path_factory.mktemp("refs")
+    a = [("c%05d" % i, 400 + i % 300) for i in range(2500)]
+    b = list(a)
+    b[1700] = ("different", b[1700][1])
+    paths = []
+    for k, contigs in enumerate((a, a, b)):
+        recs = bw.random_records(contigs, 3000, seed=20 + k, read_len=(30, 120))
+        p = str(d / f"s{k}.bam")
+        with open(p, "wb") as f:
+            f.write(bw.bgzf(bw.bam_stream(contigs, recs, text="@HD\tVN:1.6\n@PG\tID:run%d\n" % k), level=6))
+        paths.append(p)
+    return paths
+
+
+def _multi(binary, paths, extra=(), env=None):
+    return subprocess.run([binary, "contig", "-m", "mean", "covered_fraction", "-t", "3", "-b"] + paths + list(extra), capture_output=True,
+                          text=True, timeout=600, env=dict(os.environ, **(env or {})))
+
+
+def test_shared_names_across_samples_host(many_contig_pair):
+    s0, s1, sdiff = many_contig_pair
+    for paths, extra in (([s0, s1], []), ([s0, s1], ["--no-zeros"]), ([s0, sdiff], []), ([s0, s1, sdiff], ["--output-format", "sparse"])):
+        a, o = _multi(HOSTCHECK, paths, extra), _multi(ORACLE_BIN, paths, extra)
+        assert a.returncode == o.returncode, (paths, a.stderr[-300:], o.stderr[-300:])
+        assert a.stdout == o.stdout
+        if o.returncode != 0:
+            assert "Found a difference amongst the reference sets" in a.stderr and "different" in a.stderr
+
+
+@pytest.mark.gpu
+def test_shared_names_across_samples_gpu(many_contig_pair):
+    import coverm_b200
+    s0, s1, sdiff = many_contig_pair
+    for paths in ([s0, s1], [s0, sdiff]):
+        a, o = _multi(coverm_b200.COVERM_BIN, paths), _multi(ORACLE_BIN, paths)
+        assert a.returncode == o.returncode and a.stdout == o.stdout, (paths, a.stderr[-300:])
