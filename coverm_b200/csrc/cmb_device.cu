@@ -51,6 +51,7 @@ namespace {
 #include "cmb_k2.cuh"
 #include "cmb_k3.cuh"
 #include "cmb_decode.cuh"
+#include "cmb_decode_g8.cuh"
 
 // ------------------------------------------------------------------------------------------------ host context
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -744,6 +745,24 @@ constexpr size_t DEC_COPY_CHUNK = 8u << 20;    // pinned staging slot
 constexpr size_t DEC_WINDOW_BYTES = 32u << 20; // compressed bytes per copy+inflate window
 constexpr size_t DEC_SLACK = 1024;
 
+// Launch the inflate kernel over blocks [a.b0, a.b1): the four-streams-per-warp variant unless CMB_INFLATE_G8=0.
+int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st) {
+  static const bool g8 = !(getenv("CMB_INFLATE_G8") && getenv("CMB_INFLATE_G8")[0] == '0');
+  const uint32_t nb = a.b1 - a.b0;
+  if (g8) {
+    CU_TRY(c, cudaFuncSetAttribute(kd_inflate_g8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM_BYTES));
+    const uint32_t per_cta = G8_WARPS * G8_STREAMS;
+    const uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, (uint32_t)c->sm_count * 2);
+    kd_inflate_g8<<<grid, G8_WARPS * 32, G8_SMEM_BYTES, st>>>(a);
+  } else {
+    CU_TRY(c, cudaFuncSetAttribute(kd_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
+    const uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)c->sm_count * 2);
+    kd_inflate<<<grid, INF_WARPS * 32, INF_SMEM_BYTES, st>>>(a);
+  }
+  CU_TRY(c, cudaGetLastError());
+  return CMB_OK;
+}
+
 template <class T>
 int dec_grow(cmb_ctx* c, T*& p, size_t& cap, size_t need, size_t extra_bytes = 0) {
   if (cap >= need && p) return CMB_OK;
@@ -865,21 +884,20 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   CU_TRY(c, cudaMemcpyAsync(d.d_isize, in->block_isize, 4ull * nb, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemcpyAsync(d.d_ustart, ustart.data(), 8ull * (nb + 1), cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_cnt, 0, 64, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.d_status, 0, 4ull * nb, c->stream));
   CU_TRY(c, cudaMemcpyAsync(d.d_block_window, block_window.data(), 4ull * nb, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * (windows.size() + 1), c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_inflated + total, 0, DEC_SLACK, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_comp + in->size, 0, DEC_SLACK, c->stream));
   CU_TRY(c, cudaEventRecord(d.ev[1], c->stream));
-  CU_TRY(c, cudaFuncSetAttribute(kd_inflate, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)INF_SMEM_BYTES));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(d.streams[t], d.ev[1], 0));
   {  // one persistent launch over every block; its warps wait for their block's window to arrive
     InflateArgs a{};
     a.comp = d.d_comp; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
-    a.b0 = 0; a.b1 = nb; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
+    // blocks before the one holding the first record are header text the host has already read: not inflated here
+    a.b0 = first_block; a.b1 = nb; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
     a.block_window = d.d_block_window; a.ready = d.d_tickets + 1;
-    const uint32_t grid = std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)c->sm_count * 2);
-    kd_inflate<<<grid, INF_WARPS * 32, INF_SMEM_BYTES, c->stream>>>(a);
-    CU_TRY(c, cudaGetLastError());
+    if ((rc = launch_inflate(c, a, c->stream))) return rc;
   }
   std::atomic<size_t> next_window{0};
   std::atomic<int> first_err{0};
@@ -944,9 +962,9 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
     CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4, c->stream));
     InflateArgs a{};
     a.comp = d.d_comp; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
-    a.b0 = 0; a.b1 = nb; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 8;
+    a.b0 = first_block; a.b1 = nb; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 8;
     cudaEventRecord(p0, c->stream);
-    kd_inflate<<<std::min<uint32_t>((nb + INF_WARPS - 1) / INF_WARPS, (uint32_t)c->sm_count * 2), INF_WARPS * 32, INF_SMEM_BYTES, c->stream>>>(a);
+    if ((rc = launch_inflate(c, a, c->stream))) return rc;
     cudaEventRecord(p1, c->stream);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     float ms = 0;
@@ -1002,7 +1020,7 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
     memset(&zs, 0, sizeof zs);
     inflateInit2(&zs, -15);
     uint32_t bad = 0;
-    for (uint32_t b = 0; b < nb; ++b) {
+    for (uint32_t b = first_block; b < nb; ++b) {
       const uint32_t isz = in->block_isize[b];
       if (!isz) continue;
       if (tmp.size() < isz) tmp.resize(isz);
@@ -1020,7 +1038,7 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
       }
     }
     inflateEnd(&zs);
-    fprintf(stderr, "#decode_verify\t%u of %u blocks differ from zlib; %u inflated on the host\n", bad, nb, out->n_blocks_host);
+    fprintf(stderr, "#decode_verify\t%u of %u blocks differ from zlib; %u inflated on the host\n", bad, nb - first_block, out->n_blocks_host);
   }
   // ---- record chain
   WalkArgs wa{};
