@@ -2,7 +2,8 @@
 // boundaries and reduces every record to the cmb_read_batch tuple K1 consumes.  Replaces, for the stream (non-pair) path,
 // htslib's bgzf_read + bam_read1 behind BamFileNamedReader::read (bam_generator.rs:103-134).
 //
-//   KD1 kd_inflate   one warp per BGZF block (RFC 1951).  All 32 lanes run the decoder redundantly (uniform control
+//   KD1 kd_inflate   one warp per BGZF block (RFC 1951); the default is kd_inflate_g8 (cmb_decode_g8.cuh, four blocks per
+//                    warp), this one-stream-per-warp form stays selectable with CMB_INFLATE_G8=0.  All 32 lanes run the decoder redundantly (uniform control
 //                    flow), which turns the lanes into resources: the compressed bytes are held as a 2 x 128-byte
 //                    register window fetched with coalesced loads and read with shuffles; length/distance base tables
 //                    live one entry per lane; LZ77 matches are copied by all lanes; Huffman tables (10-bit root + 5-bit

@@ -44,7 +44,7 @@ def test_kernels_are_sm_100a_with_tma(lib):
     out = subprocess.run(["cuobjdump", "-sass", coverm_b200.LIB_PATH], capture_output=True, text=True).stdout
     assert "sm_100a" in out
     assert "UTMALDG" in out, "K2 must stage its tiles with TMA (cp.async.bulk.tensor)"
-    for k in ("k1_filter_accumulate", "k1b_local", "k1b_apply", "k2_scan_reduce", "k3_finalize", "kd_inflate", "kd_guess", "kd_walk",
+    for k in ("k1_filter_accumulate", "k1b_local", "k1b_apply", "k2_scan_reduce", "k3_finalize", "kd_inflate", "kd_inflate_g8", "kd_guess", "kd_walk",
               "kd_extract"):
         assert k in out
 
