@@ -282,7 +282,7 @@ def main():
         tm = ctx.timing()
         k0_ms.append(tm["ms_zero"]); k1_ms.append(tm["ms_accumulate"]); k2_ms.append(tm["ms_scan"]); k3_ms.append(tm["ms_finalize"])
         dev_ms.append(tm["ms_total"])
-        launches += tm["k1_launches"] + 2 + tm["k2_launches"] + tm["k3_launches"]
+        launches += 2 * tm["k1_launches"] + 2 + tm["k2_launches"] + tm["k3_launches"]  # K1 + K1c per batch, K1b x2, K2, K3
     with torch.cuda.stream(stream):
         ev1.record()
     torch.cuda.synchronize()
@@ -335,7 +335,7 @@ def main():
     e2e_value = total_reads / e2e_s
     h2d = s0["h2d_bytes"]  # device decode: the BGZF bytes + block table; host decode: 40 B/record + 8 B/interval tuples
     d2h = row_bytes
-    e2e_launches = s0["decode_launches"] + s0["k1_launches"] + 2 + s0["k2_launches"] + s0["k3_launches"]
+    e2e_launches = s0["decode_launches"] + 2 * s0["k1_launches"] + 2 + s0["k2_launches"] + s0["k3_launches"]
 
     # ---------------------------------------------------------------- CPU baseline + parity check on the bounded sample
     cpu = None
@@ -367,7 +367,7 @@ def main():
                                                                "decode_host_blocks", "decode_copy_inflate_ms", "decode_chain_ms",
                                                                "decode_extract_ms"]},
                     "step_walls_s": step_walls, "gpu_launches_per_step": int(e2e_launches),
-                    "decode": "device (kd_inflate/kd_guess/kd_walk/kd_extract: compressed BGZF bytes cross PCIe)" if s0["device_decode"] else "host pipeline (tuples cross PCIe)",
+                    "decode": "device (kd_inflate_g8/kd_guess/kd_walk/kd_extract: compressed BGZF bytes cross PCIe)" if s0["device_decode"] else "host pipeline (tuples cross PCIe)",
                     "input": f"BAM bytes ({len(bam_bytes)} B) in pinned host memory, cmbh_run (== `coverm contig`), TSV text out"},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k2_scan_reduce<HIST,CLEAN>", "achieved": achieved, "peak": peak, "unit": "GB/s",
