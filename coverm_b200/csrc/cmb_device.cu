@@ -776,7 +776,26 @@ int dec_grow(cmb_ctx* c, T*& p, size_t& cap, size_t need, size_t extra_bytes = 0
 }
 }  // namespace
 
+namespace {
+int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out);
+}
+// Device memory for the decode buffers (compressed file + inflated stream + tuples) is requested before anything is
+// accumulated, so running out of it simply declines the sample: the host decoder needs only the staging batches.
 extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) {
+  const int rc = submit_bgzf_impl(c, in, out);
+  if (rc == CMB_E_NOMEM) {
+    cudaGetLastError();
+    auto& d = c->dec;  // give the big buffers back so that the rest of the sample has room
+    cudaFree(d.d_comp); d.d_comp = nullptr; d.comp_cap = 0;
+    cudaFree(d.d_inflated); d.d_inflated = nullptr; d.infl_cap = 0;
+    cudaFree(d.d_tuple_slab); d.d_tuple_slab = nullptr; d.tuple_slab_bytes = 0;
+    cudaFree(d.d_rec_off); d.d_rec_off = nullptr; d.rec_cap = 0;
+    return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: not enough device memory for device-side decode");
+  }
+  return rc;
+}
+namespace {
+int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) {
   if (!c || !in || !out || !in->data || !in->block_coffset || !in->block_clen || !in->block_isize)
     return fail(c, CMB_E_ARG, "cmb_submit_bgzf: null argument");
   if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: no sample in progress");
@@ -798,6 +817,9 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   if (in->records_at == total) return CMB_OK;  // header only
   uint32_t first_block = (uint32_t)(std::upper_bound(ustart.begin(), ustart.end(), in->records_at) - ustart.begin()) - 1;
   // ---- buffers
+  if (const char* lim = getenv("CMB_DECODE_MEM_LIMIT_MB")) {  // testing aid: behave as if the device had this much room
+    if ((in->size + total) >> 20 > strtoull(lim, nullptr, 10)) return CMB_E_NOMEM;
+  }
   size_t dummy_cap;
   int rc;
   if ((rc = dec_grow(c, d.d_comp, d.comp_cap, (size_t)in->size + DEC_SLACK))) return rc;
@@ -1129,3 +1151,4 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   cudaEventElapsedTime(&out->ms_total, d.ev[0], d.ev[4]);
   return CMB_OK;
 }
+}  // namespace

@@ -156,6 +156,16 @@ def test_host_decode_path_matches_oracle(synth, which, argv):
     assert any(l.startswith("#pipeline") for l in g.stderr.splitlines())
 
 
+def test_device_decode_declines_when_memory_is_short(synth):
+    """Not enough device memory for the decode buffers -> the sample is declined before anything is accumulated and the
+    host decoder takes over (same table)."""
+    g = _assert_same(["contig", "-m", "mean", "trimmed_mean", "count", "-b", synth["small"], synth["tiny"]],
+                     env={"CMB_PIPELINE_STATS": "1", "CMB_DECODE_MEM_LIMIT_MB": "8"})
+    lines = g.stderr.splitlines()
+    assert any(l.startswith("#device_decode\tdeclined") and "not enough device memory" in l for l in lines), lines[-6:]
+    assert any(l.startswith("#pipeline") for l in lines)
+
+
 def test_host_decode_path_matches_reference_goldens():
     for case in GPU_CASES[:12]:
         check_case(case, run_case(coverm_b200.COVERM_BIN, case, extra_args=["-t", "4"], env={"CMB_HOST_DECODE": "1"}))
