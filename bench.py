@@ -254,20 +254,39 @@ def main():
     ctx.set_params(prm)
     stream = torch.cuda.ExternalStream(ctx.stream())
     row_bytes = len(lens) * C_sizeof(ContigStats)
-    gathered = torch.empty(world * row_bytes, dtype=torch.uint8, device="cuda") if world > 1 else None
+    # N > 1: the single collective of the path is the all-gather of the per-contig table over NVLink.  The rows are
+    # snapshotted on the ctx stream (the next sample re-zeroes them) and gathered from the snapshot on NCCL's stream while
+    # the next sample's kernels run; two snapshot/gather buffers, and every gather is waited for inside the timed region.
+    gathered = [torch.empty(world * row_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+    snap = [torch.empty(row_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
+    pending = [None, None]
+    step_no = [0]
 
     def device_step():
         ctx.begin_sample()
         ctx.submit_device_batch(batch, n_rec, n_iv)
         ptr = ctx.end_sample_device()  # K1c/K1b/K2/K3 + error check (stream-synchronous)
-        if world > 1:  # the single collective of the path: all-gather of the per-contig table over NVLink
-            dist.all_gather_into_tensor(gathered, _device_view(ptr, row_bytes, local_rank))
+        if world > 1:
+            k = step_no[0] & 1
+            step_no[0] += 1
+            with torch.cuda.stream(stream):
+                if pending[k] is not None:
+                    pending[k].wait()  # the gather that last used this buffer pair (two samples ago)
+                snap[k].copy_(_device_view(ptr, row_bytes, local_rank), non_blocking=True)
+                pending[k] = dist.all_gather_into_tensor(gathered[k], snap[k], async_op=True)
         return ptr
+
+    def drain_gathers():
+        for k in (0, 1):
+            if pending[k] is not None:
+                pending[k].wait()
+                pending[k] = None
+        torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
     for _ in range(max(3, args.warmup)):
         device_step()
-    torch.cuda.synchronize()
+    drain_gathers()
     barrier()
     sampler.start()
     k2_ms, k1_ms, k3_ms, k0_ms, dev_ms = [], [], [], [], []
@@ -285,11 +304,16 @@ def main():
         launches += tm["k1_launches"] + 3 + tm["k2_launches"] + tm["k3_launches"]  # K1 per batch, K1c, K1b x2, K2, K3
     with torch.cuda.stream(stream):
         ev1.record()
-    torch.cuda.synchronize()
+    drain_gathers()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
+    if world > 1:  # the gathered table holds this rank's rows where they belong
+        k_last = (step_no[0] - 1) & 1
+        mine = gathered[k_last][rank * row_bytes:(rank + 1) * row_bytes]
+        if not torch.equal(mine, snap[k_last]):
+            raise SystemExit(f"rank {rank}: all-gathered table does not contain this rank's rows")
     barrier()
     event_ms = ev0.elapsed_time(ev1)
-    # the all-gather (N > 1) runs on torch's stream after the ctx stream has been synchronised: use the wall clock then
+    # N > 1: the gathers run on NCCL's stream and are drained before the clock stops: use the wall clock then
     step_ms = max_over_ranks((wall_ms if world > 1 else event_ms) / args.steps)
     total_reads = sum_over_ranks(float(n_rec))
     value = total_reads / (step_ms * 1e-3)
