@@ -261,6 +261,7 @@ def main():
     snap = [torch.empty(row_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
     pending = [None, None]
     step_no = [0]
+    row_views = {}
 
     def device_step():
         ctx.begin_sample()
@@ -272,7 +273,9 @@ def main():
             with torch.cuda.stream(stream):
                 if pending[k] is not None:
                     pending[k].wait()  # the gather that last used this buffer pair (two samples ago)
-                snap[k].copy_(_device_view(ptr, row_bytes, local_rank), non_blocking=True)
+                if ptr not in row_views:  # the library's row table lives at a fixed address between set_reference calls
+                    row_views[ptr] = _device_view(ptr, row_bytes, local_rank)
+                snap[k].copy_(row_views[ptr], non_blocking=True)
                 pending[k] = dist.all_gather_into_tensor(gathered[k], snap[k], async_op=True)
         return ptr
 
