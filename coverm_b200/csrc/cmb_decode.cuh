@@ -60,6 +60,8 @@ struct InflateArgs {
   // (written by the copy stream after the window's bytes; NULL = everything is resident)
   const uint32_t* block_window;
   const uint32_t* ready;
+  // optional indirection: ticket t in [b0, b1) names block block_list[t] (second pass over the blocks the first declined)
+  const uint32_t* block_list;
 };
 
 // The compressed stream seen through a 64-bit bit buffer; words come from a per-lane register window.
@@ -419,6 +421,7 @@ __global__ void __launch_bounds__(INF_WARPS * 32, 2) kd_inflate(const InflateArg
     if (lane == 0) b = a.b0 + atomicAdd(a.ticket, 1u);
     b = __shfl_sync(FULL, b, 0);
     if (b >= a.b1) break;
+    if (a.block_list) b = a.block_list[b];
     bool arrived = true;
     if (a.ready) {
       const volatile uint32_t* flag = a.ready + a.block_window[b];

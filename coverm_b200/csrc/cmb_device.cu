@@ -746,8 +746,9 @@ constexpr size_t DEC_WINDOW_BYTES = 32u << 20; // compressed bytes per copy+infl
 constexpr size_t DEC_SLACK = 1024;
 
 // Launch the inflate kernel over blocks [a.b0, a.b1): the four-streams-per-warp variant unless CMB_INFLATE_G8=0.
-int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st) {
-  static const bool g8 = !(getenv("CMB_INFLATE_G8") && getenv("CMB_INFLATE_G8")[0] == '0');
+int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool allow_g8 = true) {
+  static const bool g8_default = !(getenv("CMB_INFLATE_G8") && getenv("CMB_INFLATE_G8")[0] == '0');
+  const bool g8 = g8_default && allow_g8 && !a.block_list;
   const uint32_t nb = a.b1 - a.b0;
   if (g8) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_g8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM_BYTES));
@@ -1000,9 +1001,11 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
   uint32_t h_cnt[16];
   CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
-  if (h_cnt[0]) {
+  if (h_cnt[0] || getenv("CMB_DECODE_RETRY_TEST")) {
     std::vector<uint32_t> status(nb);
     CU_TRY(c, cudaMemcpy(status.data(), d.d_status, 4ull * nb, cudaMemcpyDeviceToHost));
+    if (getenv("CMB_DECODE_RETRY_TEST"))  // testing aid: pretend every 7th block was declined by the first pass (code 29)
+      for (uint32_t b = first_block; b < nb; b += 7) status[b] = 29;
     if (getenv("CMB_DECODE_VERIFY")) {
       uint32_t hist[32] = {0};
       for (uint32_t b = 0; b < nb; ++b) hist[std::min<uint32_t>(status[b], 31)]++;
@@ -1010,6 +1013,30 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
       for (int k = 0; k < 32; ++k)
         if (hist[k]) fprintf(stderr, "\t%d:%u", k, hist[k]);
       fprintf(stderr, "\n");
+    }
+    // Second chance on the device: the one-stream-per-warp kernel has larger Huffman tables (10-bit roots, 128 long-code
+    // prefixes) than the four-streams-per-warp one, so most blocks the first pass declined for table space fit there.
+    {
+      std::vector<uint32_t> again;
+      for (uint32_t b = first_block; b < nb; ++b)
+        if (status[b] != INF_OK) again.push_back(b);
+      if (!again.empty()) {
+        uint32_t* d_list = d.d_dirty;  // free until the record chain starts (nb entries)
+        CU_TRY(c, cudaMemcpyAsync(d_list, again.data(), 4ull * again.size(), cudaMemcpyHostToDevice, c->stream));
+        CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4, c->stream));
+        CU_TRY(c, cudaMemsetAsync(d.d_cnt, 0, 4, c->stream));
+        InflateArgs a2{};
+        a2.comp = d.d_comp; a2.coff = d.d_coff; a2.clen = d.d_clen; a2.isize = d.d_isize; a2.uoff = d.d_ustart;
+        a2.b0 = 0; a2.b1 = (uint32_t)again.size(); a2.out = d.d_inflated; a2.status = d.d_status; a2.ticket = d.d_tickets;
+        a2.fail_count = d.d_cnt + 0; a2.block_list = d_list;
+        if ((rc = launch_inflate(c, a2, c->stream, false))) return rc;
+        out->n_launches += 1;
+        for (uint32_t b : again) status[b] = INF_OK;  // refreshed from the device below
+        std::vector<uint32_t> st2(nb);
+        CU_TRY(c, cudaMemcpyAsync(st2.data(), d.d_status, 4ull * nb, cudaMemcpyDeviceToHost, c->stream));
+        CU_TRY(c, cudaStreamSynchronize(c->stream));
+        for (uint32_t b : again) status[b] = st2[b];
+      }
     }
     std::vector<uint8_t> tmp(65536 + 64);
     z_stream zs;

@@ -156,6 +156,17 @@ def test_host_decode_path_matches_oracle(synth, which, argv):
     assert any(l.startswith("#pipeline") for l in g.stderr.splitlines())
 
 
+def test_declined_blocks_get_a_second_device_pass(synth):
+    """Blocks the four-streams-per-warp kernel declines are retried with the one-stream-per-warp kernel (larger tables)
+    before the host's zlib is asked; CMB_DECODE_RETRY_TEST marks every 7th block as declined to exercise that path."""
+    g = _assert_same(["contig", "-m", "mean", "trimmed_mean", "count", "-b", synth["small"]],
+                     env={"CMB_PIPELINE_STATS": "1", "CMB_DECODE_VERIFY": "1", "CMB_DECODE_RETRY_TEST": "1"})
+    st = _decode_stats(g)
+    assert any(l.startswith("#decode_status") and "\t29:" in l for l in st), st
+    assert any(l.startswith("#device_decode\tblocks=") and "host_blocks=0" in l for l in st), st
+    assert any(l.startswith("#decode_verify\t0 of ") for l in st), st
+
+
 def test_device_decode_declines_when_memory_is_short(synth):
     """Not enough device memory for the decode buffers -> the sample is declined before anything is accumulated and the
     host decoder takes over (same table)."""
