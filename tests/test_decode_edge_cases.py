@@ -138,3 +138,77 @@ def test_shared_names_across_samples_gpu(many_contig_pair):
     for paths in ([s0, s1], [s0, sdiff]):
         a, o = _multi(coverm_b200.COVERM_BIN, paths), _multi(ORACLE_BIN, paths)
         assert a.returncode == o.returncode and a.stdout == o.stdout, (paths, a.stderr[-300:])
+
+
+# ---- record-level oddities the filters and the delta accumulation must treat exactly like the reference
+def _odd_records():
+    contigs = [("one", 1), ("short", 40), ("mid", 3000), ("unused", 500)]
+    R = bw.record
+    recs = [
+        R(0, 0, [("M", 1)], qname="on_len1"),
+        R(0, 0, [("M", 30)], qname="overhang_len1"),                       # runs off a 1-base contig
+        R(1, 39, [("M", 20)], qname="last_base"),                          # starts on the last base
+        R(1, 5, [("S", 10), ("M", 10), ("H", 3)], qname="clips", tags=[("NM", "C", 0)]),
+        R(2, 10, [("M", 50)], l_seq=0, qname="star_seq", tags=[("NM", "C", 2)]),   # SEQ '*': l_seq 0 -> aligned / 0 in the filters
+        R(2, 20, [("I", 30)], qname="insert_only", tags=[("NM", "C", 30)]),        # no reference-consuming op at all
+        R(2, 30, [("M", 10), ("D", 2990)], qname="deletion_to_end", tags=[("NM", "S", 2990)]),
+        R(2, 40, [("M", 100)], mapq=255, qname="mapq255"),
+        R(2, 50, [("M", 100)], mapq=0, qname="mapq0", tags=[("NM", "I", 70000)]),  # NM larger than the alignment
+        R(2, 60, [("=", 40), ("X", 1), ("=", 59)], flag=99, mtid=2, mpos=200, tlen=240, qname="pair1", tags=[("NM", "C", 1)]),
+        R(2, 200, [("M", 100)], flag=147, mtid=2, mpos=60, tlen=-240, qname="pair1", tags=[("NM", "C", 0)]),
+        R(2, 300, [("M", 100)], flag=0x4 | 0x1 | 0x40, qname="unmapped_placed"),   # flag says unmapped but it carries a position
+        R(2, 310, [], flag=0x4, l_seq=20, qname="unmapped_no_cigar"),
+        R(2, 400, [("M", 100)], flag=0x100, qname="secondary"),
+        R(2, 500, [("M", 100)], flag=0x800, qname="supplementary"),
+        R(2, 2950, [("M", 100)], qname="overhang_mid"),
+        R(-1, -1, [], flag=0x4 | 0x1 | 0x40, l_seq=30, qname="unmapped_tail1"),
+        R(-1, -1, [], flag=0x4 | 0x1 | 0x80, l_seq=30, qname="unmapped_tail2"),
+    ]
+    return contigs, recs
+
+
+ODD_ARGS = [
+    [],
+    ["--min-read-percent-identity", "95"],
+    ["--min-read-aligned-percent", "50", "--min-read-aligned-length", "20"],
+    ["--min-mapq", "1"],
+    ["--proper-pairs-only"],
+    ["--include-secondary", "--exclude-supplementary"],
+    ["--contig-end-exclusion", "0", "--trim-min", "0", "--trim-max", "1"],
+    ["--contig-end-exclusion", "20"],
+]
+
+
+@pytest.fixture(scope="module")
+def odd_bam(tmp_path_factory):
+    contigs, recs = _odd_records()
+    p = str(tmp_path_factory.mktemp("odd") / "odd.bam")
+    with open(p, "wb") as f:
+        f.write(bw.bgzf(bw.bam_stream(contigs, recs), level=6, block_sizes=(60, 700), seed=2))
+    return p
+
+
+def _odd(binary, path, extra, env=None):
+    return subprocess.run([binary, "contig", "-m", "mean", "trimmed_mean", "covered_fraction", "covered_bases", "variance", "rpkm", "tpm",
+                           "--min-covered-fraction", "0", "-b", path, "-t", "2", "--print-reads-mapped"] + extra,
+                          capture_output=True, text=True, timeout=300, env=dict(os.environ, **(env or {})))
+
+
+@pytest.mark.parametrize("extra", ODD_ARGS, ids=[" ".join(a) or "defaults" for a in ODD_ARGS])
+def test_record_oddities_host(odd_bam, extra):
+    a, o = _odd(HOSTCHECK, odd_bam, extra), _odd(ORACLE_BIN, odd_bam, extra)
+    assert a.returncode == o.returncode, (a.stderr[-400:], o.stderr[-400:])
+    assert a.stdout == o.stdout
+    assert [l for l in a.stderr.splitlines() if l.startswith("#reads")] == [l for l in o.stderr.splitlines() if l.startswith("#reads")]
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("extra", ODD_ARGS, ids=[" ".join(a) or "defaults" for a in ODD_ARGS])
+def test_record_oddities_gpu(odd_bam, extra):
+    import coverm_b200
+    o = _odd(ORACLE_BIN, odd_bam, extra)
+    for env in ({}, {"CMB_HOST_DECODE": "1"}):
+        g = _odd(coverm_b200.COVERM_BIN, odd_bam, extra, env=env)
+        assert g.returncode == o.returncode, (env, g.stderr[-400:], o.stderr[-400:])
+        assert g.stdout == o.stdout, env
+        assert [l for l in g.stderr.splitlines() if l.startswith("#reads")] == [l for l in o.stderr.splitlines() if l.startswith("#reads")]
