@@ -13,8 +13,14 @@ struct cmbh_session {
 namespace {
 std::string g_err;
 // An ostream buffer that grows a malloc'd array and hands it over (the table text reaches the caller without a copy).
-class MallocBuf : public std::streambuf {
+class MallocBuf : public std::streambuf, public BulkSink {
  public:
+  char* append_uninitialized(size_t n) override {
+    reserve(n_ + n + 1);
+    char* at = p_ + n_;
+    n_ += n;
+    return at;
+  }
   ~MallocBuf() override { free(p_); }
   char* release(size_t* len) {
     if (!p_) reserve(1);

@@ -41,3 +41,22 @@ def test_many_contig_table_path_matches_oracle(extra, threads):
     assert a.stdout == b.stdout
     rm = lambda p: [l for l in p.stderr.splitlines() if l.startswith("#reads_mapped")]
     assert rm(a) == rm(b)
+
+
+def test_in_memory_sink_bulk_path_through_the_c_abi():
+    """cmbh_run's in-memory output sink takes formatted row blocks in parallel (more than one 4096-row block): the text
+    must equal the CLI's and the oracle's.  Uses the emulator build of the same ABI (no GPU)."""
+    import numpy as np
+
+    import coverm_b200
+    from case_runner import DATA, ORACLE_BIN
+    lib = coverm_b200.load_library(os.path.join(ROOT, "oracle", "libcoverm_hostcheck.so"))
+    sess = coverm_b200.Session(device=0, threads=4, lib=lib)
+    bam = os.path.join(DATA, "eg2.bam")
+    argv = ["contig", "-m", "mean", "trimmed_mean", "covered_fraction", "-b", bam, "-t", "4"]
+    r1 = sess.run(argv)
+    r2 = sess.run(argv, memory_inputs={bam: np.fromfile(bam, dtype=np.uint8)})  # second sample reuses the parsed reference list
+    sess.close()
+    want = subprocess.run([ORACLE_BIN] + argv, capture_output=True, text=True, check=True).stdout
+    assert r1.status == 0 and r1.out == want and r2.out == want
+    assert r1.out_len == len(want.encode())
