@@ -8,10 +8,14 @@
 // GPU, against the oracle through the real library.
 #include <cmath>
 #include <cstdlib>
+#include <algorithm>
+#include <climits>
 #include <cstring>
 #include <map>
 #include <string>
 #include <vector>
+
+#include <zlib.h>
 
 #include "../include/coverm_b200.h"
 
@@ -198,10 +202,113 @@ int cmb_submit_batch(cmb_ctx* c, uint32_t n, uint32_t ni) {
 int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* b, uint32_t n, uint32_t ni) { return submit(c, *b, n, ni); }
 void* cmb_host_alloc(size_t bytes) { return malloc(bytes ? bytes : 1); }
 void cmb_host_free(void* p) { free(p); }
-// The emulator has no device-side decoder: always decline, so the host decode pipeline is what the CPU tests exercise.
-int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input*, cmb_bgzf_result*) {
-  if (c) c->err = "device emulator: no device-side decode";
-  return CMB_E_DECLINED;
+// cmb_submit_bgzf.  By default the emulator declines, so that the CPU tests exercise the host decode pipeline; with
+// CMB_EMU_BGZF=1 it plays the device-side decoder with zlib and a plain record walk (BAM spec, SAMv1 section 4.2), which
+// lets the host's device-decode branch (block table, records_at, counters, fallback on CMB_E_DECLINED) run without a GPU.
+int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) {
+  if (!c || !in || !out) return CMB_E_ARG;
+  if (!getenv("CMB_EMU_BGZF")) {
+    c->err = "device emulator: no device-side decode";
+    return CMB_E_DECLINED;
+  }
+  if (c->mode.filter_pairs) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: pair filtering needs host mate matching");
+  *out = cmb_bgzf_result{};
+  std::vector<uint8_t> stream;
+  for (uint32_t b = 0; b < in->n_blocks; ++b) {
+    const uint32_t isz = in->block_isize[b];
+    const size_t at = stream.size();
+    stream.resize(at + isz);
+    if (!isz) continue;
+    z_stream zs;
+    memset(&zs, 0, sizeof zs);
+    if (inflateInit2(&zs, -15) != Z_OK) return fail(c, CMB_E_NOMEM, "zlib");
+    zs.next_in = const_cast<Bytef*>(in->data + in->block_coffset[b]);
+    zs.avail_in = in->block_clen[b];
+    zs.next_out = stream.data() + at;
+    zs.avail_out = isz;
+    const int zr = inflate(&zs, Z_FINISH);
+    inflateEnd(&zs);
+    uint32_t want;
+    memcpy(&want, in->data + in->block_coffset[b] + in->block_clen[b], 4);
+    if (zr != Z_STREAM_END || zs.avail_out != 0 || (uint32_t)crc32(0, stream.data() + at, isz) != want)
+      return fail(c, CMB_E_DECLINED, "emulator: BGZF block does not inflate");
+  }
+  auto u32 = [&](size_t o) { uint32_t v; memcpy(&v, stream.data() + o, 4); return v; };
+  auto u16 = [&](size_t o) { uint16_t v; memcpy(&v, stream.data() + o, 2); return (uint32_t)v; };
+  std::vector<int32_t> tid, pos, ivs, ivl;
+  std::vector<uint16_t> flag;
+  std::vector<uint8_t> mapq, nm_state;
+  std::vector<uint32_t> nm, l_seq, aligned, del, ins, iv_begin;
+  size_t o = in->records_at;
+  while (o < stream.size()) {
+    if (o + 36 > stream.size()) return fail(c, CMB_E_DECLINED, "emulator: record cut short");
+    const uint32_t bs = u32(o);
+    if (bs < 32 || o + 4 + (size_t)bs > stream.size()) return fail(c, CMB_E_DECLINED, "emulator: record cut short");
+    const size_t r = o + 4, end = r + bs;
+    const uint32_t l_name = stream[r + 8], n_cig = u16(r + 12), ls = u32(r + 16);
+    tid.push_back((int32_t)u32(r));
+    pos.push_back((int32_t)u32(r + 4));
+    mapq.push_back(stream[r + 9]);
+    flag.push_back((uint16_t)u16(r + 14));
+    l_seq.push_back(ls);
+    if (!(flag.back() & 0x900)) out->n_primary += 1;
+    size_t cg = r + 32 + l_name;
+    size_t aux = cg + 4ull * n_cig + (ls + 1) / 2 + ls;
+    if (aux > end) return fail(c, CMB_E_DECLINED, "emulator: malformed record");
+    iv_begin.push_back((uint32_t)ivs.size());
+    uint32_t al = 0, dl = 0, in_ = 0;
+    int64_t cur = pos.back();
+    for (uint32_t k = 0; k < n_cig; ++k) {
+      const uint32_t v = u32(cg + 4 * k), op = v & 15, len = v >> 4;
+      if (op == 0 || op == 7 || op == 8) {
+        ivs.push_back(cur < 0 ? -1 : (int32_t)std::min<int64_t>(cur, INT32_MAX));
+        ivl.push_back((int32_t)len);
+        cur += len;
+        al += len;
+      } else if (op == 2) { cur += len; dl += len; al += len; }
+      else if (op == 3) cur += len;
+      else if (op == 1) { in_ += len; al += len; }
+    }
+    aligned.push_back(al);
+    del.push_back(dl);
+    ins.push_back(in_);
+    uint8_t st = 0;
+    uint32_t nmv = 0;
+    while (aux + 3 <= end) {
+      const uint8_t t0 = stream[aux], t1 = stream[aux + 1], ty = stream[aux + 2];
+      aux += 3;
+      size_t sz;
+      if (ty == 'A' || ty == 'c' || ty == 'C') sz = 1;
+      else if (ty == 's' || ty == 'S') sz = 2;
+      else if (ty == 'i' || ty == 'I' || ty == 'f') sz = 4;
+      else if (ty == 'Z' || ty == 'H') { size_t e = aux; while (e < end && stream[e]) ++e; sz = e < end ? e - aux + 1 : end - aux; }
+      else if (ty == 'B') {
+        if (aux + 5 > end) sz = end - aux;
+        else { const uint8_t sub = stream[aux]; const uint32_t cnt = u32(aux + 1); sz = 5 + (size_t)cnt * ((sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4); }
+      } else return fail(c, CMB_E_DECLINED, "emulator: unknown aux type");
+      if (t0 == 'N' && t1 == 'M' && st == 0) {
+        if (ty == 'C') { st = 1; nmv = stream[aux]; }
+        else if (ty == 'S') { st = 1; nmv = u16(aux); }
+        else if (ty == 'I') { st = 1; nmv = u32(aux); }
+        else st = 2;
+      }
+      aux += sz;
+    }
+    nm_state.push_back(st);
+    nm.push_back(nmv);
+    o = end;
+  }
+  iv_begin.push_back((uint32_t)ivs.size());
+  out->n_records = tid.size();
+  out->n_intervals = ivs.size();
+  out->h2d_bytes = in->size;
+  if (tid.empty()) return CMB_OK;
+  if (ivs.empty()) { ivs.push_back(0); ivl.push_back(0); }
+  cmb_read_batch b{};
+  b.tid = tid.data(); b.pos = pos.data(); b.flag = flag.data(); b.mapq = mapq.data(); b.nm_state = nm_state.data(); b.nm = nm.data();
+  b.l_seq = l_seq.data(); b.aligned = aligned.data(); b.del = del.data(); b.ins = ins.data(); b.iv_begin = iv_begin.data();
+  b.iv_start = ivs.data(); b.iv_len = ivl.data();
+  return submit(c, b, (uint32_t)tid.size(), (uint32_t)out->n_intervals);
 }
 
 int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** out) {

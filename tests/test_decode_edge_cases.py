@@ -85,6 +85,12 @@ def test_host_decoder_edge_cases(files, name):
     _same(_run(HOSTCHECK, files[name], threads="3"), _run(ORACLE_BIN, files[name]), name)
 
 
+@pytest.mark.parametrize("name", NAMES)
+def test_device_decode_branch_edge_cases(files, name):
+    """The host's device-decode branch with the emulator as the decoder (CMB_EMU_BGZF=1): declines must fall back cleanly."""
+    _same(_run(HOSTCHECK, files[name], env={"CMB_EMU_BGZF": "1", "CMB_PIPELINE_STATS": "1"}, threads="3"), _run(ORACLE_BIN, files[name]), name)
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("name", NAMES)
 def test_device_decoder_edge_cases(files, name):

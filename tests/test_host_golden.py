@@ -60,3 +60,10 @@ def test_in_memory_sink_bulk_path_through_the_c_abi():
     want = subprocess.run([ORACLE_BIN] + argv, capture_output=True, text=True, check=True).stdout
     assert r1.status == 0 and r1.out == want and r2.out == want
     assert r1.out_len == len(want.encode())
+
+
+# The host's device-decode branch (DeviceSession::process handing the BGZF bytes to cmb_submit_bgzf and falling back when it
+# declines) with the emulator playing the device decoder (CMB_EMU_BGZF=1): same goldens, no GPU.
+@pytest.mark.parametrize("case", HOST_CASES, ids=[f"{c['sub']}@{c['ref']}" for c in HOST_CASES])
+def test_device_decode_branch_matches_reference_golden(case):
+    check_case(case, run_case(HOSTCHECK, case, extra_args=["-t", "2"], env={"CMB_EMU_BGZF": "1"}))
