@@ -691,9 +691,14 @@ __global__ void __launch_bounds__(256) kd_extract(const ExtractArgs a) {
     uint32_t iv = a.iv_begin[i];
     const uint32_t iv_end = a.iv_begin[i + 1];
     uint32_t aligned = 0, del = 0, ins = 0;
+    bool placeholder = false;
     if (aux > end) {
       err |= DEC_ERR_RECORD;
     } else {
+      if (n_cigar) {
+        const uint32_t v0 = ldu32(cig);
+        placeholder = (v0 & 0xf) == 4 && (v0 >> 4) == l_seq && tid >= 0 && pos >= 0;
+      }
       long long cursor = pos;
       for (uint32_t k = 0; k < n_cigar; ++k) {
         const uint32_t v = ldu32(cig + 4 * k);
@@ -754,6 +759,9 @@ __global__ void __launch_bounds__(256) kd_extract(const ExtractArgs a) {
         else if (ty == 'I') { nm_state = 1; nm = ldu32(p); }
         else nm_state = 2;
       }
+      // A CG:B,I tag behind a `<l_seq>S...` placeholder is the real CIGAR of a read with > 65535 operations (htslib
+      // bam_tag2cigar): its intervals do not fit the n_cigar_op reservation, so the stream goes to the host decoder.
+      if (t0 == 'C' && t1 == 'G' && ty == 'B' && placeholder) err |= DEC_ERR_RECORD;
       p += sz;
     }
     a.nm_state[i] = (uint8_t)nm_state;

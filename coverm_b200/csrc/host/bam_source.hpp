@@ -267,6 +267,76 @@ inline uint16_t rd_u16(const uint8_t* p) {
   return v;
 }
 
+
+// ---- record layout checks shared by every host decoder -------------------------------------------------------------
+// htslib's bam_read1 rejects a record whose fixed-size fields do not fit its block_size (the reference then panics with
+// "Error reading BAM record", contig.rs:113-115); the CIGAR / aux walks below rely on that having been checked.
+// It also restores CIGARs of more than 65535 operations from the CG:B,I tag (bam_tag2cigar: the in-record CIGAR is then the
+// placeholder `<l_seq>S<reflen>N`).  `rec` points at block_size and the whole record is in memory.
+struct CigarView {
+  const uint8_t* ops = nullptr;  // n little-endian u32 operations (len << 4 | op)
+  uint32_t n = 0;
+  bool valid = false;            // false: the fixed fields overrun block_size
+};
+inline CigarView effective_cigar(const uint8_t* rec) {
+  CigarView v;
+  const uint32_t block_size = rd_u32(rec);
+  const uint8_t* o = rec + 4;
+  const uint32_t l_read_name = o[8], n_cigar = rd_u16(o + 12), l_seq = rd_u32(o + 16);
+  const uint64_t fixed = 32ull + l_read_name + 4ull * n_cigar + ((uint64_t)l_seq + 1) / 2 + l_seq;
+  if (block_size < 32 || fixed > block_size) return v;
+  v.valid = true;
+  v.ops = o + 32 + l_read_name;
+  v.n = n_cigar;
+  if (n_cigar == 0) return v;
+  const uint32_t op0 = rd_u32(v.ops);
+  if ((op0 & 0xf) != 4 || (op0 >> 4) != l_seq) return v;  // not the placeholder: the common case ends here
+  if ((int32_t)rd_u32(o) < 0 || (int32_t)rd_u32(o + 4) < 0) return v;
+  const uint8_t* a = o + fixed;
+  const uint8_t* end = o + block_size;
+  while (a + 3 <= end) {  // bam_aux_get(b, "CG")
+    const uint8_t t0 = a[0], t1 = a[1], ty = a[2];
+    a += 3;
+    size_t sz;
+    switch (ty) {
+      case 'A': case 'c': case 'C': sz = 1; break;
+      case 's': case 'S': sz = 2; break;
+      case 'i': case 'I': case 'f': sz = 4; break;
+      case 'Z': case 'H': {
+        const uint8_t* e = (const uint8_t*)memchr(a, 0, (size_t)(end - a));
+        sz = e ? (size_t)(e - a) + 1 : (size_t)(end - a);
+        break;
+      }
+      case 'B': {
+        if (a + 5 > end) return v;
+        const uint8_t sub = a[0];
+        const uint32_t cnt = rd_u32(a + 1);
+        const size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
+        sz = 5 + es * (size_t)cnt;
+        if (t0 == 'C' && t1 == 'G') {
+          if ((sub == 'I' || sub == 'i') && cnt >= n_cigar && cnt < (1u << 29) && a + sz <= end) {
+            v.ops = a + 5;
+            v.n = cnt;
+          }
+          return v;
+        }
+        break;
+      }
+      default: return v;  // the NM walk raises the unknown-aux-type error
+    }
+    a += sz;
+  }
+  return v;
+}
+[[noreturn]] inline void throw_bad_record_layout() {
+  throw Panic("Error reading BAM record: the record's name, CIGAR and sequence fields do not fit its block_size");
+}
+// Upper bound of the intervals a record can produce (the operation count of its effective CIGAR); -1: invalid layout.
+inline int64_t record_cigar_ops(const uint8_t* rec) {
+  const CigarView v = effective_cigar(rec);
+  return v.valid ? (int64_t)v.n : -1;
+}
+
 // Decode the fixed fields, CIGAR summary and NM aux of one BAM record (`rec` points at block_size).
 // Intervals (M/=/X blocks, contig.rs:171-186) are appended to iv_start/iv_len.
 inline void decode_bam_record(const uint8_t* rec, Tuple& t, std::vector<int32_t>& iv_start, std::vector<int32_t>& iv_len) {
@@ -281,11 +351,13 @@ inline void decode_bam_record(const uint8_t* rec, Tuple& t, std::vector<int32_t>
   t.flag = rd_u16(o + 14);
   t.l_seq = rd_u32(o + 16);
   t.mtid = (int32_t)rd_u32(o + 20);
+  const CigarView cv = effective_cigar(rec);
+  if (!cv.valid) throw_bad_record_layout();
   const uint8_t* cig = o + 32 + l_read_name;
   uint32_t aligned = 0, del = 0, ins = 0, n_iv = 0;
   int64_t cursor = t.pos;
-  for (uint32_t i = 0; i < n_cigar; ++i) {
-    const uint32_t v = rd_u32(cig + 4 * i);
+  for (uint32_t i = 0; i < cv.n; ++i) {
+    const uint32_t v = rd_u32(cv.ops + 4 * (size_t)i);
     const uint32_t op = v & 0xf, len = v >> 4;
     switch (op) {
       case 0: case 7: case 8:  // M = X

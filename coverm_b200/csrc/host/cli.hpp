@@ -31,7 +31,7 @@ struct CliOptions {
   uint64_t contig_end_exclusion = 75;
   std::string output_format = "dense";
   std::optional<std::string> output_file, separator, genome_definition, lib_estimators, lib_flags;
-  bool single_genome = false, lib_streaming = false, print_reads_mapped = false, timing = false;
+  bool single_genome = false, lib_streaming = false, print_reads_mapped = false, timing = false, quiet = false;
   int threads = 1;
   int device = 0;
 };
@@ -111,7 +111,8 @@ inline CliOptions parse_cli(const std::vector<std::string>& args) {
     else if (a == "--lib-streaming") o.lib_streaming = true;
     else if (a == "--print-reads-mapped") o.print_reads_mapped = true;
     else if (a == "--timing") o.timing = true;
-    else if (a == "-q" || a == "--quiet" || a == "-v" || a == "--verbose") {}
+    else if (a == "-q" || a == "--quiet") o.quiet = true;
+    else if (a == "-v" || a == "--verbose") {}
     else usage("unexpected argument '" + a + "' found");
   }
   if (!o.lib_flags && !o.proper_pairs_only &&
@@ -333,7 +334,7 @@ inline CliResult run_cli(const std::vector<std::string>& args, const std::vector
     }
     plan.printer.pool = &session->pool();
     const double t_driver0 = now_s();
-    DriverIO io{session, plan.params, &res.timings, &res.record_counts};
+    DriverIO io{session, plan.params, &res.timings, &res.record_counts, o.quiet ? nullptr : &err};
     if (o.sub == "contig") {
       res.reads_mapped = contig_coverage(inputs, taker, plan.estimators, !o.no_zeros, io);
     } else {

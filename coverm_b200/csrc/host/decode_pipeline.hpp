@@ -102,11 +102,13 @@ inline uint32_t decode_bam_record_into(const uint8_t* rec, Tuple& t, int32_t* iv
   t.flag = rd_u16(o + 14);
   t.l_seq = rd_u32(o + 16);
   t.mtid = (int32_t)rd_u32(o + 20);
+  const CigarView cv = effective_cigar(rec);  // layout check + CG:B,I long-CIGAR restoration (bam_source.hpp)
+  if (!cv.valid) throw_bad_record_layout();
   const uint8_t* cig = o + 32 + l_read_name;
   uint32_t aligned = 0, del = 0, ins = 0, n_iv = 0;
   int64_t cursor = t.pos;
-  for (uint32_t i = 0; i < n_cigar; ++i) {
-    const uint32_t v = rd_u32(cig + 4 * i);
+  for (uint32_t i = 0; i < cv.n; ++i) {
+    const uint32_t v = rd_u32(cv.ops + 4 * (size_t)i);
     const uint32_t op = v & 0xf, len = v >> 4;
     switch (op) {
       case 0: case 7: case 8:

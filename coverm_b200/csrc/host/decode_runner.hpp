@@ -171,7 +171,9 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
         if (w.stitched.size() < need) swallowed = true;
         else {
           it.have_stitched = true;
-          ub_iv += rd_u16(w.stitched.data() + 4 + 12);
+          const int64_t ops = record_cigar_ops(w.stitched.data());
+          if (ops < 0) throw_bad_record_layout();
+          ub_iv += (uint64_t)ops;
         }
       }
     }
@@ -188,7 +190,9 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
         if (bs < 32) throw Panic("Error reading BAM record: corrupt block_size");
         if (pos + 4 + (size_t)bs > usize) break;
         w.offs.push_back((uint32_t)pos);
-        ub_iv += rd_u16(buf + pos + 4 + 12);
+        const int64_t ops = record_cigar_ops(buf + pos);
+        if (ops < 0) throw_bad_record_layout();
+        ub_iv += (uint64_t)ops;
         pos += 4 + (size_t)bs;
       }
       carry.assign(buf + pos, buf + usize);
@@ -293,8 +297,13 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
     while (pos + 4 <= usize) {
       const uint32_t bs = rd_u32(buf + pos);
       if (bs < 32 || pos + 4 + (size_t)bs > usize) break;
+      const int64_t ops = record_cigar_ops(buf + pos);
+      if (ops < 0) {  // fields overrun the record: let the chain step raise the error
+        w.offs.clear();
+        return;
+      }
       w.offs.push_back((uint32_t)pos);
-      ub += rd_u16(buf + pos + 4 + 12);
+      ub += (uint64_t)ops;
       pos += 4 + (size_t)bs;
     }
     if (pos + 4 <= usize && rd_u32(buf + pos) < 32) {  // corrupt chain: let the chain step raise the error

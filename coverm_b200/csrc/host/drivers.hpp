@@ -109,7 +109,23 @@ struct DriverIO {
   cmb_params params;  // FlagFilter + filter thresholds + E + trim + want
   std::vector<SampleTiming>* timings = nullptr;
   std::vector<uint64_t>* record_counts = nullptr;
+  std::ostream* log = nullptr;  // the reference's info!/warn! lines (env_logger on stderr); null = --quiet
 };
+
+// contig.rs:233-240, genome.rs:309-316, 784-791: `info!("In sample '{}', found {} reads mapped out of {} total ({:.*}%)", ..)`
+// and the contig driver's warning about a sample without primary alignments (contig.rs:243-248).
+inline void log_reads_mapped(const DriverIO& io, const std::string& stoit_name, const ReadsMapped& rm, bool warn_if_none) {
+  if (!io.log) return;
+  char pct[64];
+  const double num = (double)(rm.num_mapped_reads * 100ull), den = (double)rm.num_reads;
+  if (rm.num_reads == 0) snprintf(pct, sizeof pct, "%s", rm.num_mapped_reads == 0 ? "NaN" : "inf");  // Rust Display of f64
+  else snprintf(pct, sizeof pct, "%.2f", num / den);
+  *io.log << "[INFO] In sample '" << stoit_name << "', found " << rm.num_mapped_reads << " reads mapped out of " << rm.num_reads
+          << " total (" << pct << "%)\n";
+  if (warn_if_none && rm.num_reads == 0)
+    *io.log << "[WARN] No primary alignments were observed for sample " << stoit_name
+            << " - perhaps something went wrong in the mapping?\n";
+}
 
 inline SampleResult run_sample(const DriverIO& io, const InputSpec& in) {
   SampleResult r = io.session->process(in, io.params);
@@ -187,6 +203,7 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
       }
       host_stat("contig.taker_feed", host_now() - t_feed0);
       reads_mapped_vector.push_back({num_mapped_reads_total, r.num_detected_primary_alignments});
+      log_reads_mapped(io, r.stoit_name, reads_mapped_vector.back(), true);
       continue;
     }
     for (uint32_t tid = 0; tid < n; ++tid) {
@@ -214,6 +231,7 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
       for (auto& e : coverage_estimators) e.setup();
     }
     reads_mapped_vector.push_back({num_mapped_reads_total, r.num_detected_primary_alignments});
+    log_reads_mapped(io, r.stoit_name, reads_mapped_vector.back(), true);
   }
   return reads_mapped_vector;
 }
@@ -284,6 +302,7 @@ inline std::vector<ReadsMapped> mosdepth_genome_coverage_with_contig_names(
       }
     }
     reads_mapped_vector.push_back({num_mapped_reads_total, r.num_detected_primary_alignments});
+    log_reads_mapped(io, r.stoit_name, reads_mapped_vector.back(), false);
   }
   return reads_mapped_vector;
 }
@@ -444,6 +463,7 @@ inline std::vector<ReadsMapped> mosdepth_genome_coverage(const std::vector<Input
       if (finish_genome(pending, last_genome, unobs, std::string(), n - 1)) num_mapped_reads_total += reads_in_genome;
     }
     reads_mapped_vector.push_back({num_mapped_reads_total, r.num_detected_primary_alignments});
+    log_reads_mapped(io, r.stoit_name, reads_mapped_vector.back(), false);
   }
   return reads_mapped_vector;
 }

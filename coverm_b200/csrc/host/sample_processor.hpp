@@ -399,7 +399,9 @@ class DeviceSession {
         if (bs < 32) throw Panic("Error reading BAM record: corrupt block_size");
         if (q + 4 + (size_t)bs > buf.size()) break;
         rec_off.push_back(q);
-        max_iv += rd_u16(buf.data() + q + 4 + 12);
+        const int64_t ops = record_cigar_ops(buf.data() + q);
+        if (ops < 0) throw_bad_record_layout();
+        max_iv += (size_t)ops;
         q += 4 + (size_t)bs;
         if (rec_off.size() == batch_records_ / 2) break;  // keep one window within a batch
       }

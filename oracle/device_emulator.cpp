@@ -292,6 +292,9 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
         else if (ty == 'I') { st = 1; nmv = u32(aux); }
         else st = 2;
       }
+      // like kd_extract: a CG:B,I tag behind a `<l_seq>S...` placeholder (long CIGAR) goes to the host decoder
+      if (t0 == 'C' && t1 == 'G' && ty == 'B' && n_cig && (u32(cg) & 15) == 4 && (u32(cg) >> 4) == ls && tid.back() >= 0 && pos.back() >= 0)
+        return fail(c, CMB_E_DECLINED, "emulator: long CIGAR in a CG tag");
       aux += sz;
     }
     nm_state.push_back(st);

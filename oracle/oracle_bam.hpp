@@ -269,6 +269,10 @@ class AlignmentFile {
     r.l_seq = u32(o + 16);
     r.mtid = i32(o + 20);
     o += 32;
+    // htslib bam_read1: the fixed-size fields must fit block_size (sam.c bam_read1 returns -4), which the reference turns
+    // into a panic (contig.rs:113-115)
+    if (block_size < 32 || 32ull + l_read_name + 4ull * n_cigar + ((uint64_t)r.l_seq + 1) / 2 + r.l_seq > block_size)
+      throw Panic("Error reading BAM record: the record's name, CIGAR and sequence fields do not fit its block_size");
     r.qname.assign((const char*)data_.data() + o, l_read_name ? l_read_name - 1 : 0);
     o += l_read_name;
     r.cigar.resize(n_cigar);
@@ -278,10 +282,14 @@ class AlignmentFile {
       r.cigar[i].len = v >> 4;
     }
     o += 4 * (size_t)n_cigar;
-    o += (r.l_seq + 1) / 2 + r.l_seq;
+    o += ((size_t)r.l_seq + 1) / 2 + r.l_seq;
+    // htslib bam_tag2cigar (called by bam_read1): a `<l_seq>S<reflen>N` placeholder CIGAR plus a CG:B,I tag is a read with
+    // more than 65535 CIGAR operations; the tag's array replaces the in-record CIGAR.
+    const bool placeholder = n_cigar > 0 && r.tid >= 0 && r.pos >= 0 && r.cigar[0].op == 4 && r.cigar[0].len == r.l_seq;
     // aux scan for NM (record.aux("NM"), lib.rs:139)
     r.nm_state = 0;
     r.nm = 0;
+    bool cg_seen = false;
     while (o + 3 <= end) {
       char t0 = data_[o], t1 = data_[o + 1], ty = data_[o + 2];
       o += 3;
@@ -302,6 +310,17 @@ class AlignmentFile {
           uint32_t cnt = u32(o + 1);
           size_t es = (sub == 'c' || sub == 'C') ? 1 : (sub == 's' || sub == 'S') ? 2 : 4;
           sz = 5 + es * (size_t)cnt;
+          if (t0 == 'C' && t1 == 'G' && !cg_seen) {
+            cg_seen = true;
+            if (placeholder && (sub == 'I' || sub == 'i') && cnt >= n_cigar && cnt < (1u << 29) && o + sz <= end) {
+              r.cigar.resize(cnt);
+              for (uint32_t i = 0; i < cnt; ++i) {
+                uint32_t v = u32(o + 5 + 4 * (size_t)i);
+                r.cigar[i].op = v & 0xf;
+                r.cigar[i].len = v >> 4;
+              }
+            }
+          }
           break;
         }
         default: throw Panic("Error reading BAM record: bad aux type");

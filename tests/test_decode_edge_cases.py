@@ -4,6 +4,7 @@ compression with overlapping LZ77 copies, tiny and random BGZF block sizes (reco
 a truncated file and a corrupted block.  The CPU half runs the product's host decoder (with the test-only device emulator)
 against the oracle; the GPU half runs the CUDA path twice — device-side decode and CMB_HOST_DECODE=1 — against the oracle."""
 import os
+import struct
 import subprocess
 
 import pytest
@@ -50,7 +51,35 @@ def _files(tmp_path_factory):
     put("corrupt_block", bytes(bad))
     signed_nm = bw.bam_stream(CONTIGS, [bw.record(1, 10, [("M", 100)], tags=[("NM", "c", 1)])])
     put("nm_signed_type", bw.bgzf(signed_nm, level=6))
+    # fixed-size fields that overrun block_size (htslib's bam_read1 fails, the reference panics): an inflated n_cigar_op
+    # and an inflated l_read_name, each in the middle of an otherwise healthy stream
+    for name, field_off, fmt, value in (("bad_n_cigar", 4 + 12, "<H", 40000), ("bad_l_read_name", 4 + 8, "<B", 250)):
+        recs = bw.random_records(CONTIGS, 800, seed=31)
+        victim = bytearray(bw.record(1, 100, [("M", 60)], qname="v"))
+        victim[field_off:field_off + struct.calcsize(fmt)] = struct.pack(fmt, value)
+        recs = sorted(recs[:400], key=lambda r: struct.unpack_from("<ii", r, 4)) + [bytes(victim)] + recs[400:]
+        put(name, bw.bgzf(bw.bam_stream(CONTIGS, recs), level=6, block_sizes=(3000, 20000), seed=12))
+    put("long_cigar_cg", bw.bgzf(bw.bam_stream(CONTIGS, _long_cigar_records()), level=6))
     return out
+
+
+LONG_OPS = 70001  # > 65535: stored as `<l_seq>S<reflen>N` + CG:B,I (SAMv1 4.2.2); htslib restores it when reading
+
+
+def _long_cigar_records():
+    ops = []
+    for k in range(LONG_OPS // 2):
+        ops += [("M", 3), ("I", 1)]
+    ops.append(("M", 3))
+    l_seq = sum(n for c, n in ops if c in "MI")
+    reflen = sum(n for c, n in ops if c == "M")
+    cg = [(n << 4) | bw.CIGAR_OPS.index(c) for c, n in ops]
+    recs = [bw.record(0, 5, [("M", 100)], qname="before"),
+            bw.record(3, 1000, [("S", l_seq), ("N", reflen)], qname="ultralong", tags=[("NM", "I", LONG_OPS // 2), ("CG", "B", ("I", cg))]),
+            # the same shape WITHOUT a CG tag is just a soft-clipped read with a skip: no coverage
+            bw.record(3, 2000, [("S", 50), ("N", 500)], qname="plain_placeholder_shape"),
+            bw.record(4, 10, [("M", 100)], qname="after")]
+    return recs
 
 
 @pytest.fixture(scope="module")
@@ -59,8 +88,9 @@ def files(tmp_path_factory):
 
 
 NAMES = ["level0_stored", "level1", "level9_random_blocks", "tiny_blocks", "no_eof_empty_blocks", "homopolymer_level9", "long_reads",
-         "long_reads_level0", "rich_tags", "no_records", "one_record", "truncated", "corrupt_block", "nm_signed_type", "cut_mid_record"]
-FAILING = {"truncated", "corrupt_block", "nm_signed_type", "cut_mid_record"}
+         "long_reads_level0", "rich_tags", "no_records", "one_record", "truncated", "corrupt_block", "nm_signed_type", "cut_mid_record",
+         "bad_n_cigar", "bad_l_read_name", "long_cigar_cg"]
+FAILING = {"truncated", "corrupt_block", "nm_signed_type", "cut_mid_record", "bad_n_cigar", "bad_l_read_name"}
 
 
 def _run(binary, path, env=None, threads="4"):
@@ -83,6 +113,24 @@ def test_host_decoder_edge_cases(files, name):
     if not os.path.exists(HOSTCHECK):
         subprocess.check_call(["make", "-C", os.path.join(ROOT, "oracle")])
     _same(_run(HOSTCHECK, files[name], threads="3"), _run(ORACLE_BIN, files[name]), name)
+
+
+def test_long_cigar_is_restored_from_the_cg_tag(files):
+    """htslib (bam_tag2cigar) swaps the CG:B,I array in for the placeholder CIGAR: the 35 001 M blocks of 3 bases must be counted."""
+    for binary in (ORACLE_BIN, HOSTCHECK):
+        p = subprocess.run([binary, "contig", "-m", "covered_bases", "count", "--contig-end-exclusion", "0", "-b", files["long_cigar_cg"], "-t", "2"],
+                           capture_output=True, text=True, timeout=300)
+        assert p.returncode == 0, p.stderr[-500:]
+        rows = dict(l.split("\t", 1) for l in p.stdout.splitlines()[1:])
+        assert rows["ctgD"] == "%d\t2" % (3 * (LONG_OPS // 2 + 1)), (binary, rows)
+        assert rows["ctgA"] == "100\t1" and rows["ctgE"] == "100\t1"
+
+
+def test_malformed_record_layout_is_a_read_error(files):
+    for name in ("bad_n_cigar", "bad_l_read_name"):
+        for binary in (ORACLE_BIN, HOSTCHECK):
+            p = _run(binary, files[name], threads="3")
+            assert p.returncode == 101 and "Error reading BAM record" in p.stderr, (name, binary, p.returncode, p.stderr[-300:])
 
 
 @pytest.mark.parametrize("name", NAMES)
