@@ -1,19 +1,27 @@
 #!/usr/bin/env python
-"""bench.py — reads/sec of `coverm contig -m mean trimmed_mean covered_fraction` (BASELINE.json configs[1]).
+"""bench.py — reads/sec of the `coverm contig|genome --bam-files` coverage hot path (BASELINE.json).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--config 2|ns|3]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
-One "step" = one pass of the coverage hot path over one synthetic sample (500 000 contigs / ~10 M records).
-  value   whole-job reads/s with the per-read tuples already resident in HBM (device arm: K0 zero-fill of the row
-          table, K1 filter+delta, K1b chunk carries, K2 TMA-staged segmented scan + reductions, K3 per-contig finalise;
-          for N > 1 also the NCCL all-gather of the per-contig table), timed with CUDA events on the library's stream.
-  e2e     the same metric through the public C ABI call a user makes (cmbh_run == `coverm contig ... -b sample.bam`):
-          BAM bytes in a HOST buffer -> BGZF inflate + BAM decode on the host cores -> pinned SoA tuples -> H2D ->
-          kernels -> D2H of the table -> printed TSV in a host buffer.  Wall clock, everything inside.
-  roofline / cpu_baseline as described in DESIGN.md §Measurement.
-`--impl reference` times the CPU restatement of the reference (oracle/, all host threads for BGZF inflate, the record
-loop single-threaded exactly as the reference's) on a bounded sample of the same workload.
+Workloads (`--config`, all synthetic; the default is BASELINE.json configs[1]):
+  2    coverm contig -m mean trimmed_mean covered_fraction, 500 000 contigs / ~2.8 Gbp / ~10.5 M records
+  ns   the north-star target: the same command on a ~5 Gbp / ~52 M-record BAM (906 000 contigs)
+  3    coverm genome -s '~' -m mean trimmed_mean covered_fraction --min-read-percent-identity 95,
+       1000 MAGs / 200 000 contigs / ~52 M records
+
+One "step" = one pass of the hot path over one sample.
+  value     whole-job reads/s with the per-read tuples already resident in HBM: K1 filter + delta accumulation, K1b chunk
+            carries, K2 TMA-staged segmented scan + reductions, K3 per-contig finalise (N > 1: plus the collective of the
+            path), timed with CUDA events on the library's stream.  It explains the kernels; it is NOT the speed-up.
+  e2e       the same metric through the public C ABI call a user makes (cmbh_run == `coverm ...  -b sample.bam`): BAM
+            bytes in pinned HOST memory -> H2D of the compressed file -> device inflate + record decode -> kernels -> D2H of the
+            per-contig table -> printed TSV in a host buffer.  Wall clock, everything inside, every step.  `cold_cli` is
+            one fresh `bin/coverm` process on the same file (CUDA context, allocations, header parse, file read included).
+  parity    the e2e output of the FULL file compared as text with the CPU oracle's output of the same file.
+  roofline / cpu_baseline as described in DESIGN.md (Measurement).
+`--impl reference` times the CPU restatement of the reference (oracle/, all host threads for BGZF inflate, the record loop
+single-threaded exactly as the reference's) on the SAME file and command; one step = one full run.
 """
 import argparse
 import json
@@ -26,10 +34,16 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-METRIC = "reads/sec `coverm contig` (mean+trimmed_mean+covered_fraction)"
-METHODS = ["mean", "trimmed_mean", "covered_fraction"]
-CONTIG_END_EXCLUSION = 75
-TRIM = (0.05, 0.95)
+GEN_CONTIG = ["--median-len", "4000", "--sigma", "0.8", "--min-len", "1000", "--max-len", "2000000"]
+CONFIGS = {
+    "2": {"label": "configs[1]", "sub": "contig", "contigs": 500000, "reads": 10000000, "gen": GEN_CONTIG,
+          "methods": ["mean", "trimmed_mean", "covered_fraction"], "extra": []},
+    "ns": {"label": "north_star target (5 Gbp / 50 M reads)", "sub": "contig", "contigs": 906000, "reads": 50000000,
+           "gen": GEN_CONTIG, "methods": ["mean", "trimmed_mean", "covered_fraction"], "extra": []},
+    "3": {"label": "configs[2]", "sub": "genome", "contigs": 200000, "reads": 50000000,
+          "gen": ["--genomes", "1000", "--median-len", "15000", "--sigma", "0.8", "--min-len", "1000", "--max-len", "2000000"],
+          "methods": ["mean", "trimmed_mean", "covered_fraction"], "extra": ["-s", "~", "--min-read-percent-identity", "95"]},
+}
 
 
 def log(*a):
@@ -38,7 +52,7 @@ def log(*a):
 
 def effective_cpus():
     """CPUs this process may actually use: the smaller of the visible CPUs and the cgroup CPU quota
-    (the GPU boxes expose 128 logical CPUs but cap the container at 24 via cpu.max; more threads only get throttled)."""
+    (the GPU boxes expose 128 logical CPUs but cap the container via cpu.max; more threads only get throttled)."""
     n = os.cpu_count() or 1
     try:
         n = min(n, len(os.sched_getaffinity(0)))
@@ -56,7 +70,7 @@ def effective_cpus():
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(p):
-        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        return float(json.load(open(p))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst: K2 is timed as a single launch)"
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
@@ -90,52 +104,68 @@ class ClockSampler(threading.Thread):
                 "samples": len(s)}
 
 
-def gen_bam(path, contigs, reads, seed, threads):
+def gen_bam(path, cfg, contigs, reads, seed, threads):
     import coverm_b200
     t = time.time()
     meta = path + ".json"
-    if os.path.exists(path) and os.path.exists(meta):  # same (contigs, reads, seed) already generated in this workdir
+    key = [contigs, reads, seed] + cfg["gen"]
+    if os.path.exists(path) and os.path.exists(meta):  # same workload already generated in this workdir
         info = json.load(open(meta))
-        if info.get("key") == [contigs, reads, seed]:
+        if info.get("key") == key:
             info["gen_s"] = 0.0
             return info
     out = subprocess.run([coverm_b200.BAMGEN_BIN, "--out", path, "--contigs", str(contigs), "--reads", str(reads), "--seed",
-                          str(seed), "--median-len", "4000", "--sigma", "0.8", "--min-len", "1000", "--max-len", "2000000",
-                          "--threads", str(threads)], capture_output=True, text=True, check=True).stdout
+                          str(seed), "--threads", str(threads)] + cfg["gen"], capture_output=True, text=True, check=True).stdout
     info = json.loads(out)
     info["gen_s"] = round(time.time() - t, 2)
     info["bam_bytes"] = os.path.getsize(path)
-    info["key"] = [contigs, reads, seed]
+    info["key"] = key
     json.dump(info, open(meta, "w"))
     return info
 
 
-def coverm_argv(bam, threads):
-    return ["contig", "-m"] + METHODS + ["-b", bam, "-t", str(threads)]
+def coverm_argv(cfg, bam, threads):
+    return [cfg["sub"], "-m"] + cfg["methods"] + cfg["extra"] + ["-b", bam, "-t", str(threads)]
 
 
-def run_reference_arm(args, workdir, threads):
-    """The reference's CPU path (oracle restatement) on a bounded sample: 1/10 of the contigs and reads."""
-    contigs, reads = max(1, args.contigs // args.cpu_fraction), max(1, args.reads // args.cpu_fraction)
-    bam = os.path.join(workdir, f"cpu_sample_{contigs}_{reads}.bam")
-    info = gen_bam(bam, contigs, reads, args.seed + 100, threads)
+def workload_config(cfg, args, info, world, scaling):
+    """The `config` object: a description of the WORKLOAD, identical for our arm and the reference arm (same file, same
+    command, same N)."""
+    if world == 1:
+        par = "1 sample on 1 GPU"
+    elif scaling == "weak":
+        par = f"{world} samples, one per GPU; all-gather of the per-contig table"
+    else:
+        par = f"1 sample, contigs range-partitioned over {world} GPUs (each rank decodes its own BGZF block range); all-gather of the per-contig table"
+    return {"workload": f"{cfg['label']}: coverm {cfg['sub']} -m {' '.join(cfg['methods'])} {' '.join(cfg['extra'])}".rstrip() +
+                        f" on a synthetic reference-sorted BAM, {args.contigs} contigs / {info['bases']} bp / {info['records']} records",
+            "config_id": args.config, "contigs": args.contigs, "reads": int(info["records"]), "bases": int(info["bases"]),
+            "bam_bytes": int(info["bam_bytes"]), "seed": args.seed, "parallelism": par,
+            "l2": f"inputs larger than L2 (126 MB), no flush needed: {4 * info['bases'] / 1e9:.1f} GB delta arena (4 B per reference base) + "
+                  f"{48.5 * info['records'] / 1e6:.0f} MB tuples per step; e2e additionally streams the {info['bam_bytes'] / 1e9:.2f} GB file"}
+
+
+def run_oracle(cfg, bam, threads, runs, warmup):
+    """oracle/coverm_oracle (the CPU restatement of the reference) on `bam`: (mean seconds per run, stdout of the last run)."""
     oracle = os.path.join(ROOT, "oracle", "coverm_oracle")
-    argv = [oracle] + coverm_argv(bam, threads)
-    outs = []
-    times = []
-    for i in range(args.warmup_cpu + args.steps_cpu):
+    argv = [oracle] + coverm_argv(cfg, bam, threads)
+    times, out = [], None
+    for i in range(warmup + runs):
         t = time.perf_counter()
         p = subprocess.run(argv, capture_output=True, text=True, check=True)
         dt = time.perf_counter() - t
-        if i >= args.warmup_cpu:
+        if i >= warmup:
             times.append(dt)
-        outs.append(p.stdout)
-    sec = sum(times) / len(times)
-    return {"value": info["records"] / sec, "unit": "reads/s", "cores": threads, "kind": "port",
-            "sample": f"{contigs} contigs / {info['bases']} bp / {info['records']} records (1/{args.cpu_fraction} of the workload, "
-                      f"same generator), oracle/coverm_oracle -t {threads}: {threads} BGZF inflate threads, single-threaded record loop "
-                      f"+ one O(L) pass per estimator as in the reference; mean of {len(times)} runs",
-            "seconds_per_run": sec}, bam, outs[-1]
+        out = p.stdout
+        log(f"oracle run {i + 1}/{warmup + runs}: {dt:.2f} s")
+    return sum(times) / len(times), out
+
+
+def cpu_baseline_entry(records, sec, threads, runs, what):
+    return {"value": records / sec, "unit": "reads/s", "cores": threads, "kind": "port",
+            "sample": f"{what}; oracle/coverm_oracle -t {threads}: {threads} BGZF inflate threads, single-threaded record loop + one "
+                      f"O(L) pass per estimator as in the reference; mean of {runs} run(s)",
+            "seconds_per_run": sec}
 
 
 def main():
@@ -143,18 +173,22 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--config", default="2", choices=sorted(CONFIGS))
     ap.add_argument("--lib", default=None, help="bind another build of libcoverm_b200.so (kernel A/B experiments)")
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--contigs", type=int, default=500000)
-    ap.add_argument("--reads", type=int, default=10000000)
+    ap.add_argument("--contigs", type=int, default=0, help="override the workload's contig count")
+    ap.add_argument("--reads", type=int, default=0, help="override the workload's read count")
     ap.add_argument("--seed", type=int, default=20260925)
-    ap.add_argument("--cpu-fraction", type=int, default=10)
-    ap.add_argument("--steps-cpu", type=int, default=2)
-    ap.add_argument("--warmup-cpu", type=int, default=0)
+    ap.add_argument("--ref-budget-s", type=float, default=420.0, help="--impl reference: wall-clock budget for all of its runs")
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
-    ap.add_argument("--skip-cpu-baseline", action="store_true")
+    ap.add_argument("--skip-cpu-baseline", action="store_true", help="no oracle run (then no parity check and no cpu_baseline)")
+    ap.add_argument("--skip-cold-cli", action="store_true")
     ap.add_argument("--workdir", default=os.environ.get("CMB_BENCH_DIR", "/tmp/coverm_b200_bench"))
     args = ap.parse_args()
+    cfg = CONFIGS[args.config]
+    args.contigs = args.contigs or cfg["contigs"]
+    args.reads = args.reads or cfg["reads"]
+    metric = f"reads/sec `coverm {cfg['sub']}` ({'+'.join(cfg['methods'])})"
     if args.lib:
         import coverm_b200 as _cb
         _cb.LIB_PATH = os.path.abspath(args.lib)
@@ -176,16 +210,35 @@ def main():
     os.makedirs(args.workdir, exist_ok=True)
 
     if args.impl == "reference":
+        # The reference's CPU path on the SAME file and command as our arm (rank 0's sample), every run a full pass.
         if rank != 0:
             return
-        cpu, _, _ = run_reference_arm(args, args.workdir, ncpu)
-        line = {"impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": "reads/s", "n_gpus": args.gpus,
-                "steps": args.steps, "warmup": args.warmup, "ms_per_step": cpu["seconds_per_run"] * 1e3,
-                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-                "config": {"workload": f"coverm contig -m {' '.join(METHODS)} on a synthetic sorted BAM; bounded sample: {cpu['sample']}",
-                           "contigs": args.contigs // args.cpu_fraction, "reads": args.reads // args.cpu_fraction},
+        bam = os.path.join(args.workdir, f"sample_c{args.config}_r0_{args.contigs}_{args.reads}.bam")
+        info = gen_bam(bam, cfg, args.contigs, args.reads, args.seed, ncpu)
+        t0 = time.perf_counter()
+        warm = 0
+        if args.warmup > 0:  # one untimed warm-up run (page cache, CPU clocks); more would only repeat it
+            run_oracle(cfg, bam, ncpu, 1, 0)
+            warm = 1
+        times = []
+        while len(times) < args.steps:
+            elapsed = time.perf_counter() - t0
+            est = max(times) if times else (elapsed if warm else 0.0)
+            if times and elapsed + est > args.ref_budget_s:
+                break
+            times.append(run_oracle(cfg, bam, ncpu, 1, 0)[0])
+        steps = len(times)
+        sec = sum(times) / steps
+        cpu = cpu_baseline_entry(info["records"], sec, ncpu, steps, "the full workload file")
+        line = {"impl": "reference", "metric": metric, "value": cpu["value"], "unit": "reads/s", "n_gpus": args.gpus,
+                "steps": steps, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "i32", "data": "synthetic",
+                "config": workload_config(cfg, args, info, args.gpus, "weak"),
                 "cpu_baseline": cpu,
-                "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+                "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "note": f"each step is one full `coverm` run on the whole file ({sec:.1f} s); steps/warmup are what actually ran "
+                        f"inside a {args.ref_budget_s:.0f} s budget"}
         emit(line)
         return
 
@@ -193,7 +246,7 @@ def main():
     import torch
     import torch.distributed as dist
     import coverm_b200
-    from coverm_b200 import ContigStats, Params, ReadBatch
+    from coverm_b200 import ContigStats
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py --impl ours needs a CUDA device (there is no CPU fallback)")
@@ -220,8 +273,8 @@ def main():
         return float(t.item())
 
     # ---------------------------------------------------------------- workload: one sample per GPU (weak scaling)
-    bam = os.path.join(args.workdir, f"sample_r{rank}_{args.contigs}_{args.reads}.bam")
-    info = gen_bam(bam, args.contigs, args.reads, args.seed + rank, threads)
+    bam = os.path.join(args.workdir, f"sample_c{args.config}_r{rank}_{args.contigs}_{args.reads}.bam")
+    info = gen_bam(bam, cfg, args.contigs, args.reads, args.seed + rank, threads)
     log(f"rank {rank}: generated {bam}: {info}")
     # HOST buffer handed to the C ABI: the BAM file's bytes in pinned host memory (the contract's "inputs in pinned host
     # memory"); every e2e step copies them host->device again inside the timed region.
@@ -230,30 +283,26 @@ def main():
     bam_bytes = bam_pinned.numpy()
     with open(bam, "rb") as f:
         f.readinto(memoryview(bam_bytes))
-    t0 = time.time()
-    tup = coverm_b200.extract_tuples(bam, threads)
-    n_rec, n_iv = int(tup["n_records"]), int(tup["n_intervals"])
-    lens = tup["contig_len"]
-    log(f"rank {rank}: {n_rec} records, {n_iv} intervals, {len(lens)} contigs, {int(lens.sum())} bp; tuple extraction {time.time() - t0:.2f}s")
+    argv = coverm_argv(cfg, bam, threads)
+
+    # ---------------------------------------------------------------- one e2e pass: warms the session and leaves the sample's
+    # tuples in HBM (cmb_last_bgzf_batch) for the device-resident arm
+    sess = coverm_b200.Session(device=local_rank, threads=threads)
+    res = sess.run(argv, memory_inputs={bam: bam_bytes})
+    if res.status != 0:
+        raise SystemExit(f"coverm_b200 failed: {res.err}")
+    if not res.samples[0]["device_decode"]:
+        raise SystemExit("the device-side decoder declined the bench file; the device-resident arm needs its tuples in HBM")
+    n_contigs = args.contigs
+    ctx = sess.device_context()
+    ctx.n_contigs = n_contigs
+    batch, n_rec, n_iv = ctx.last_bgzf_batch()
+    assert n_rec == res.samples[0]["n_records"], (n_rec, res.samples[0]["n_records"])
+    log(f"rank {rank}: {n_rec} records, {n_iv} interval slots resident in HBM")
 
     # ---------------------------------------------------------------- device arm: tuples resident in HBM
-    dev = {k: torch.from_numpy(tup[k]).cuda() for k in ["tid", "pos", "flag", "mapq", "nm_state", "nm", "l_seq", "aligned",
-                                                         "del_", "ins", "iv_begin", "iv_start", "iv_len"]}
-    batch = ReadBatch()
-    batch.capacity_records, batch.capacity_intervals = n_rec, n_iv
-    for k, tns in dev.items():
-        setattr(batch, k, tns.data_ptr())
-    ctx = coverm_b200.DeviceContext(device=local_rank, batch_records=1 << 16, n_staging=2)
-    ctx.set_reference(lens)
-    prm = Params()
-    prm.include_improper_pairs, prm.include_supplementary, prm.include_secondary = 1, 1, 0
-    prm.filtering, prm.min_mapq = 0, 255
-    prm.contig_end_exclusion = CONTIG_END_EXCLUSION
-    prm.trim_min, prm.trim_max = TRIM
-    prm.want = 1  # CMB_WANT_HIST (trimmed_mean)
-    ctx.set_params(prm)
     stream = torch.cuda.ExternalStream(ctx.stream())
-    row_bytes = len(lens) * C_sizeof(ContigStats)
+    row_bytes = n_contigs * C_sizeof(ContigStats)
     # N > 1: the single collective of the path is the all-gather of the per-contig table over NVLink.  The rows are
     # snapshotted on the ctx stream (the next sample re-zeroes them) and gathered from the snapshot on NCCL's stream while
     # the next sample's kernels run; two snapshot/gather buffers, and every gather is waited for inside the timed region.
@@ -287,7 +336,8 @@ def main():
         torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank)
-    for _ in range(max(3, args.warmup)):
+    n_warm = max(3, args.warmup)
+    for _ in range(n_warm):
         device_step()
     drain_gathers()
     barrier()
@@ -326,20 +376,16 @@ def main():
     k2_mean = mean(k2_ms)
     algo_bytes = 4.0 * arena_elems
     achieved = algo_bytes / (k2_mean * 1e-3) / 1e9
-    traffic = None
+    traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "k2_traffic.json")
-    if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+    if os.path.exists(tpath) and args.config == "2":
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source", "profiles/k2_traffic.json (ncu --set full capture of this workload)")
 
     # ---------------------------------------------------------------- e2e arm: BAM bytes in host memory -> TSV
-    sess = coverm_b200.Session(device=local_rank, threads=threads)
-    argv = coverm_argv(bam, threads)
     e2e_steps = args.e2e_steps or args.steps
-    res = None
     for _ in range(max(1, min(2, args.warmup))):
         res = sess.run(argv, memory_inputs={bam: bam_bytes})
-    if res.status != 0:
-        raise SystemExit(f"coverm_b200 failed: {res.err}")
     torch.cuda.synchronize()
     barrier()
     t_e = time.perf_counter()
@@ -363,46 +409,61 @@ def main():
     h2d = s0["h2d_bytes"]  # device decode: the BGZF bytes + block table; host decode: 40 B/record + 8 B/interval tuples
     d2h = row_bytes
     e2e_launches = s0["decode_launches"] + s0["k1_launches"] + 3 + s0["k2_launches"] + s0["k3_launches"]
+    e2e_out = res.out  # the table of the last timed step (full file)
 
-    # ---------------------------------------------------------------- CPU baseline + parity check on the bounded sample
+    # ---------------------------------------------------------------- cold CLI: one fresh process on the same file
+    cold = None
+    if rank == 0 and world == 1 and not args.skip_cold_cli:
+        out_path = os.path.join(args.workdir, "cold_cli.tsv")
+        t_c = time.perf_counter()
+        p = subprocess.run([coverm_b200.COVERM_BIN] + argv + ["-o", out_path], capture_output=True, text=True)
+        cold_s = time.perf_counter() - t_c
+        same = p.returncode == 0 and open(out_path).read() == e2e_out
+        cold = {"seconds": cold_s, "reads_per_s": n_rec / cold_s, "output_identical_to_session_run": same,
+                "what": "one fresh `bin/coverm` process, file read from the page cache: CUDA context + arena cudaMalloc + "
+                        "tensor-map encode + header parse + decode + kernels + printing to a file"}
+        if not same:
+            log(f"cold CLI run differs or failed (rc {p.returncode}): {p.stderr[-400:]}")
+
+    # ---------------------------------------------------------------- CPU baseline + parity on the FULL file
     cpu = None
     parity = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
-        cpu, cpu_bam, oracle_out = run_reference_arm(args, args.workdir, ncpu)
-        mine = sess.run(coverm_argv(cpu_bam, threads))
-        parity = (mine.status == 0 and mine.out == oracle_out)
+        sec, oracle_out = run_oracle(cfg, bam, ncpu, 1, 0)
+        cpu = cpu_baseline_entry(n_rec, sec, ncpu, 1, "the full workload file (the same file the GPU arm ran)")
+        parity = e2e_out == oracle_out
         if not parity:
-            log("PARITY FAILURE on the bounded sample: GPU output differs from the oracle")
+            gl, ol = e2e_out.splitlines(), oracle_out.splitlines()
+            diff = [(i, a, b) for i, (a, b) in enumerate(zip(gl, ol)) if a != b][:5]
+            log(f"PARITY FAILURE on the full file: {len(gl)} vs {len(ol)} lines; first differences {diff}")
     sess.close()
 
     if rank == 0:
+        config = workload_config(cfg, args, info, world, "weak")
+        host = {"host_threads_per_rank": threads, "host_cpus_effective": ncpu, "host_cpus_visible": os.cpu_count(), "reads_per_gpu": n_rec}
         line = {
-            "metric": METRIC, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+            "metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
             "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
-            "data": "synthetic",
-            "config": {"workload": f"configs[1]: coverm contig -m {' '.join(METHODS)} on a synthetic reference-sorted BAM, "
-                                   f"{args.contigs} contigs / {info['bases']} bp / {n_rec} records per GPU (one sample per GPU)",
-                       "contigs": args.contigs, "reads_per_gpu": n_rec, "bases_per_gpu": int(info["bases"]),
-                       "parallelism": f"{world} sample(s), one per GPU" + ("; NCCL all-gather of the per-contig table" if world > 1 else ""),
-                       "l2": f"inputs larger than L2: {algo_bytes / 1e9:.1f} GB delta arena + {(39 * n_rec + 8 * n_iv) / 1e6:.0f} MB tuples per step",
-                       "host_threads_per_rank": threads, "host_cpus_effective": ncpu, "host_cpus_visible": os.cpu_count()},
-            "clocks": sampler.summary(),
+            "data": "synthetic", "config": config, "host": host, "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
-                    "seconds_per_step": e2e_s,
+                    "seconds_per_step": e2e_s, "steps": e2e_steps,
                     "breakdown_last_step": {k: s0[k] for k in ["total_s", "decode_s", "submit_wait_s", "end_sample_s", "k0_ms", "k1_ms",
                                                                "k2_ms", "k3_ms", "device_total_ms", "device_decode",
                                                                "decode_host_blocks", "decode_copy_inflate_ms", "decode_chain_ms",
                                                                "decode_extract_ms"]},
                     "step_walls_s": step_walls, "gpu_launches_per_step": int(e2e_launches),
                     "decode": "device (kd_inflate_g8/kd_guess/kd_walk/kd_extract: compressed BGZF bytes cross PCIe)" if s0["device_decode"] else "host pipeline (tuples cross PCIe)",
-                    "input": f"BAM bytes ({len(bam_bytes)} B) in pinned host memory, cmbh_run (== `coverm contig`), TSV text out"},
+                    "input": f"BAM bytes ({len(bam_bytes)} B) in pinned host memory, cmbh_run (== `coverm {cfg['sub']}`), TSV text out; "
+                             "warm session (context, arena, decode buffers and the parsed header are reused across steps)",
+                    "cold_cli": cold},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k2_scan_reduce<HIST,CLEAN>", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
+                         "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
                          "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": k2_mean},
             "device_breakdown_ms": {"k0_zero": mean(k0_ms), "k1_filter_delta+carry": mean(k1_ms), "k2_scan_reduce": k2_mean,
                                     "k3_finalize": mean(k3_ms), "stream_total": mean(dev_ms), "wall_per_step": wall_ms / args.steps},
-            "cpu_baseline": cpu, "parity_vs_oracle_on_cpu_sample": parity,
+            "cpu_baseline": cpu, "parity": parity,
+            "parity_what": "text of the e2e table of the full file == oracle/coverm_oracle's output of the same file" if parity is not None else None,
         }
         emit(line)
     if world > 1:

@@ -89,7 +89,7 @@ class HostResult(C.Structure):
 
 DEVICE_SYMBOLS = ["cmb_abi_version", "cmb_create", "cmb_destroy", "cmb_last_error", "cmb_set_reference",
                   "cmb_set_params", "cmb_begin_sample", "cmb_acquire_batch", "cmb_submit_batch",
-                  "cmb_submit_device_batch", "cmb_submit_bgzf", "cmb_end_sample", "cmb_fetch_pairs", "cmb_end_sample_device",
+                  "cmb_submit_device_batch", "cmb_submit_bgzf", "cmb_last_bgzf_batch", "cmb_end_sample", "cmb_fetch_pairs", "cmb_end_sample_device",
                   "cmb_get_timing", "cmb_stream", "cmb_host_alloc", "cmb_host_free"]
 class Tuples(C.Structure):
     _fields_ = [("n_contigs", C.c_uint32), ("contig_len", C.POINTER(C.c_uint64)), ("n_records", C.c_uint64),
@@ -100,8 +100,8 @@ class Tuples(C.Structure):
                 ("iv_start", C.POINTER(C.c_int32)), ("iv_len", C.POINTER(C.c_int32))]
 
 
-HOST_SYMBOLS = ["cmbh_session_create", "cmbh_session_destroy", "cmbh_last_error", "cmbh_session_set_shard",
-                "cmbh_run", "cmbh_free_result", "cmbh_main", "cmbh_extract_tuples", "cmbh_free_tuples"]
+HOST_SYMBOLS = ["cmbh_session_create", "cmbh_session_destroy", "cmbh_last_error", "cmbh_session_set_shard", "cmbh_session_ctx",
+                "cmbh_run", "cmbh_plan_params", "cmbh_free_result", "cmbh_main", "cmbh_extract_tuples", "cmbh_free_tuples"]
 
 
 def extract_tuples(path, threads=None):
@@ -121,6 +121,16 @@ def extract_tuples(path, threads=None):
     return out
 
 _lib = None
+
+
+def plan_params(argv):
+    """cmb_params the `coverm <argv>` command line would hand to the device library (cmbh_plan_params)."""
+    lib = load_library()
+    args = (C.c_char_p * len(argv))(*[a.encode() for a in argv])
+    prm = Params()
+    if lib.cmbh_plan_params(len(argv), args, C.byref(prm)) != 0:
+        raise CmbError("cmbh_plan_params failed: " + lib.cmbh_last_error().decode())
+    return prm
 
 
 def load_library(path=None):
@@ -159,6 +169,10 @@ def load_library(path=None):
     lib.cmbh_session_set_shard.argtypes = [C.c_void_p, C.c_uint32, C.c_uint32]
     lib.cmbh_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(MemInput), C.c_int,
                              C.POINTER(HostResult)]
+    lib.cmb_last_bgzf_batch.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.cmbh_session_ctx.argtypes = [C.c_void_p]
+    lib.cmbh_session_ctx.restype = C.c_void_p
+    lib.cmbh_plan_params.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_void_p]
     lib.cmbh_free_result.argtypes = [C.POINTER(HostResult)]
     lib.cmbh_free_result.restype = None
     lib.cmbh_extract_tuples.argtypes = [C.c_char_p, C.c_void_p, C.c_size_t, C.c_int, C.POINTER(Tuples)]
@@ -214,6 +228,10 @@ class Session:
     def set_shard(self, tid_begin, tid_end):
         self._lib.cmbh_session_set_shard(self._h, tid_begin, tid_end)
 
+    def device_context(self):
+        """The session's cmb_ctx as a (borrowed) DeviceContext: continue on the device ABI after run()."""
+        return DeviceContext(borrowed=self._lib.cmbh_session_ctx(self._h), lib=self._lib)
+
     def run(self, argv, memory_inputs=None):
         """memory_inputs: {path: bytes-like (e.g. numpy uint8 array / bytes)} read instead of the filesystem."""
         lib = self._lib
@@ -260,15 +278,25 @@ class Session:
 class DeviceContext:
     """Direct binding of the device-level ABI (cmb_*), used by bench.py for device-resident timing."""
 
-    def __init__(self, device=0, batch_records=1 << 20, batch_intervals=0, n_staging=2):
-        lib = load_library()
+    def __init__(self, device=0, batch_records=1 << 20, batch_intervals=0, n_staging=2, borrowed=None, lib=None):
+        lib = lib or load_library()
         self._lib = lib
         self._h = C.c_void_p()
+        self._owned = borrowed is None
+        self.n_contigs = 0
+        if borrowed is not None:  # a cmb_ctx* owned by someone else (Session.device_context())
+            self._h = C.c_void_p(borrowed)
+            return
         cfg = DeviceCfg(device, batch_records, batch_intervals, n_staging)
         rc = lib.cmb_create(C.byref(cfg), C.byref(self._h))
         if rc != 0:
             raise CmbError("cmb_create failed: " + lib.cmb_last_error(None).decode())
-        self.n_contigs = 0
+
+    def last_bgzf_batch(self):
+        """(ReadBatch of device pointers, n_records, n_intervals) left in HBM by the last device-side decode."""
+        b, nr, ni = ReadBatch(), C.c_uint32(), C.c_uint32()
+        self._check(self._lib.cmb_last_bgzf_batch(self._h, C.byref(b), C.byref(nr), C.byref(ni)), "cmb_last_bgzf_batch")
+        return b, nr.value, ni.value
 
     def _check(self, rc, what):
         if rc != 0:
@@ -323,9 +351,9 @@ class DeviceContext:
         return self._lib.cmb_stream(self._h)
 
     def close(self):
-        if self._h:
+        if self._h and self._owned:
             self._lib.cmb_destroy(self._h)
-            self._h = C.c_void_p()
+        self._h = C.c_void_p()
 
     def __del__(self):
         try:

@@ -133,6 +133,8 @@ struct cmb_ctx {
     size_t rec_cap = 0;
     void* d_tuple_slab = nullptr;
     size_t tuple_slab_bytes = 0;
+    uint32_t last_n_rec = 0, last_n_cig = 0;  // tuples of the last successful cmb_submit_bgzf (cmb_last_bgzf_batch)
+    bool last_valid = false;
     std::vector<void*> pinned;
     std::vector<cudaStream_t> streams;
     std::vector<cudaEvent_t> slot_events, done_events;
@@ -782,7 +784,17 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
 }
 // Device memory for the decode buffers (compressed file + inflated stream + tuples) is requested before anything is
 // accumulated, so running out of it simply declines the sample: the host decoder needs only the staging batches.
+extern "C" int cmb_last_bgzf_batch(cmb_ctx* c, cmb_read_batch* dev_batch, uint32_t* n_records, uint32_t* n_intervals) {
+  if (!c || !dev_batch || !n_records || !n_intervals) return fail(c, CMB_E_ARG, "cmb_last_bgzf_batch: null argument");
+  if (!c->dec.last_valid || !c->dec.d_tuple_slab) return fail(c, CMB_E_ARG, "cmb_last_bgzf_batch: no device-decoded sample is resident");
+  carve_batch(c->dec.d_tuple_slab, c->dec.last_n_rec, c->dec.last_n_cig, dev_batch);
+  *n_records = c->dec.last_n_rec;
+  *n_intervals = c->dec.last_n_cig;
+  return CMB_OK;
+}
+
 extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) {
+  if (c) c->dec.last_valid = false;
   const int rc = submit_bgzf_impl(c, in, out);
   if (rc == CMB_E_NOMEM) {
     cudaGetLastError();
@@ -1145,6 +1157,8 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     }
     cmb_read_batch tb;
     carve_batch(d.d_tuple_slab, (uint32_t)n_rec, (uint32_t)n_cig, &tb);
+    d.last_n_rec = (uint32_t)n_rec;
+    d.last_n_cig = (uint32_t)n_cig;
     OffsetArgs oa{};
     oa.data = d.d_inflated; oa.ustart = d.d_ustart; oa.guess = d.d_guess; oa.rec_base = d.d_rec_base; oa.cig_base = d.d_cig_base;
     oa.first_block = first_block; oa.n_blocks = nb; oa.rec_off = d.d_rec_off; oa.iv_begin = tb.iv_begin; oa.n_records = n_rec; oa.n_cig_total = n_cig;
@@ -1162,6 +1176,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     if (h_cnt[1]) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: malformed alignment record (flags %u)", h_cnt[1]);
     memcpy(&out->n_primary, h_cnt + 4, 8);
+    d.last_valid = true;
     CU_TRY(c, cudaEventRecord(d.ev[4], c->stream));
     if (c->n_local) {
       rc = launch_k1(c, tb, (uint32_t)n_rec, (uint32_t)n_cig);

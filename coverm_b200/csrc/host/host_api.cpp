@@ -96,6 +96,8 @@ int cmbh_session_set_shard(cmbh_session* s, uint32_t tid_begin, uint32_t tid_end
   return 0;
 }
 
+void* cmbh_session_ctx(cmbh_session* s) { return s ? (void*)s->dev->ctx() : nullptr; }
+
 int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_input* mem, int n_mem, cmbh_result* res) {
   if (!res || (argc > 0 && !argv)) return -2;
   memset(res, 0, sizeof *res);
@@ -150,6 +152,19 @@ int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_
     si.decode_launches = t.decode_launches;
   }
   return 0;
+}
+
+int cmbh_plan_params(int argc, const char* const* argv, void* params) {
+  if (!params || (argc > 0 && !argv)) return -2;
+  try {
+    const CliOptions o = parse_cli(std::vector<std::string>(argv, argv + argc));
+    const Plan plan = make_plan(o);
+    memcpy(params, &plan.params, sizeof(cmb_params));
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
 }
 
 void cmbh_free_result(cmbh_result* res) {

@@ -234,6 +234,10 @@ typedef struct cmb_bgzf_result {
   uint64_t h2d_bytes;             /* compressed bytes + block table copied host->device                */
 } cmb_bgzf_result;
 int cmb_submit_bgzf(cmb_ctx* ctx, const cmb_bgzf_input* in, cmb_bgzf_result* out);
+/* The tuples the last successful cmb_submit_bgzf extracted, still resident in device memory (valid until the next
+ * cmb_submit_bgzf / cmb_destroy): DEVICE pointers laid out as cmb_read_batch, ready for cmb_submit_device_batch.
+ * Lets a caller re-run the filter/scan/reduce kernels over an already decoded sample (device-only timing, parameter sweeps). */
+int cmb_last_bgzf_batch(cmb_ctx* ctx, cmb_read_batch* dev_batch, uint32_t* n_records, uint32_t* n_intervals);
 
 /* Page-locked host memory for result buffers (cmb_end_sample copies straight into it at PCIe speed).  Plain malloc
  * semantics otherwise; free with cmb_host_free. */

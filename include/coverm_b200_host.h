@@ -62,7 +62,16 @@ const char* cmbh_last_error(void);
 /* Restrict the session to contigs [tid_begin, tid_end) (multi-GPU contig sharding); rows outside come back zero. */
 int cmbh_session_set_shard(cmbh_session* s, uint32_t tid_begin, uint32_t tid_end);
 
+/* The session's device context (a cmb_ctx* of coverm_b200.h), for callers that continue on the device ABI after a
+ * cmbh_run -- e.g. re-running the kernels over the tuples the run left in HBM (cmb_last_bgzf_batch). */
+void* cmbh_session_ctx(cmbh_session* s);
+
 int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_input* mem, int n_mem, cmbh_result* res);
+/* The device parameters (cmb_params of coverm_b200.h: FlagFilter, filter thresholds, contig-end exclusion, trim bounds,
+ * wanted statistics) that `coverm <argv>` hands to the device library -- EstimatorsAndTaker / FilterParameters
+ * (src/bin/coverm.rs:1315-1504, 1648-1704) reduced to what the kernels need.  `params` points at a cmb_params.
+ * For callers that drive the device ABI themselves (bench.py's device-resident timing). */
+int cmbh_plan_params(int argc, const char* const* argv, void* params);
 void cmbh_free_result(cmbh_result* res);
 
 /* Whole-file tuple extraction on the host (no GPU): the SoA columns of cmb_read_batch for every record of a BAM/SAM

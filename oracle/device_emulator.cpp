@@ -205,6 +205,8 @@ void cmb_host_free(void* p) { free(p); }
 // cmb_submit_bgzf.  By default the emulator declines, so that the CPU tests exercise the host decode pipeline; with
 // CMB_EMU_BGZF=1 it plays the device-side decoder with zlib and a plain record walk (BAM spec, SAMv1 section 4.2), which
 // lets the host's device-decode branch (block table, records_at, counters, fallback on CMB_E_DECLINED) run without a GPU.
+int cmb_last_bgzf_batch(cmb_ctx* c, cmb_read_batch*, uint32_t*, uint32_t*) { return fail(c, CMB_E_ARG, "emulator: no device-resident tuples"); }
+
 int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) {
   if (!c || !in || !out) return CMB_E_ARG;
   if (!getenv("CMB_EMU_BGZF")) {
