@@ -183,6 +183,8 @@ def main():
     ap.add_argument("--e2e-steps", type=int, default=0, help="timed e2e steps (default: --steps)")
     ap.add_argument("--skip-cpu-baseline", action="store_true", help="no oracle run (then no parity check and no cpu_baseline)")
     ap.add_argument("--skip-cold-cli", action="store_true")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="N > 1: strong = one sample range-partitioned by contig over the N GPUs (default); weak = N samples, one per GPU")
     ap.add_argument("--workdir", default=os.environ.get("CMB_BENCH_DIR", "/tmp/coverm_b200_bench"))
     args = ap.parse_args()
     cfg = CONFIGS[args.config]
@@ -232,9 +234,9 @@ def main():
         cpu = cpu_baseline_entry(info["records"], sec, ncpu, steps, "the full workload file")
         line = {"impl": "reference", "metric": metric, "value": cpu["value"], "unit": "reads/s", "n_gpus": args.gpus,
                 "steps": steps, "warmup": warm, "steps_requested": args.steps, "warmup_requested": args.warmup,
-                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "weak",
+                "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": args.scaling if args.gpus > 1 else "weak",
                 "vs_baseline": None, "dtype": "i32", "data": "synthetic",
-                "config": workload_config(cfg, args, info, args.gpus, "weak"),
+                "config": workload_config(cfg, args, info, args.gpus, args.scaling),
                 "cpu_baseline": cpu,
                 "e2e": {"value": cpu["value"], "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "note": f"each step is one full `coverm` run on the whole file ({sec:.1f} s); steps/warmup are what actually ran "
@@ -272,74 +274,80 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.SUM)
         return float(t.item())
 
-    # ---------------------------------------------------------------- workload: one sample per GPU (weak scaling)
-    bam = os.path.join(args.workdir, f"sample_c{args.config}_r{rank}_{args.contigs}_{args.reads}.bam")
-    info = gen_bam(bam, cfg, args.contigs, args.reads, args.seed + rank, threads)
-    log(f"rank {rank}: generated {bam}: {info}")
+    # ---------------------------------------------------------------- workload
+    # N == 1: one sample on one GPU.  N > 1, --scaling strong (default): the SAME sample, contigs range-partitioned over the N GPUs
+    # (every rank decodes only its BGZF block range; one NCCL gather of the per-contig table inside the library).
+    # --scaling weak: N different samples, one per GPU, no exchange at all (replicas).
+    strong = world > 1 and args.scaling == "strong"
+    file_rank = 0 if strong else rank
+    bam = os.path.join(args.workdir, f"sample_c{args.config}_r{file_rank}_{args.contigs}_{args.reads}.bam")
+    if not strong or rank == 0:
+        info = gen_bam(bam, cfg, args.contigs, args.reads, args.seed + file_rank, ncpu if strong else threads)
+        log(f"rank {rank}: generated {bam}: {info}")
+    barrier()
+    if strong and rank != 0:
+        info = json.load(open(bam + ".json"))
     # HOST buffer handed to the C ABI: the BAM file's bytes in pinned host memory (the contract's "inputs in pinned host
-    # memory"); every e2e step copies them host->device again inside the timed region.
+    # memory"); every e2e step copies this rank's share of them host->device again inside the timed region.
     bam_size = os.path.getsize(bam)
     bam_pinned = torch.empty(bam_size, dtype=torch.uint8, pin_memory=True)
     bam_bytes = bam_pinned.numpy()
     with open(bam, "rb") as f:
         f.readinto(memoryview(bam_bytes))
     argv = coverm_argv(cfg, bam, threads)
+    file_records = int(info["records"])
 
-    # ---------------------------------------------------------------- one e2e pass: warms the session and leaves the sample's
-    # tuples in HBM (cmb_last_bgzf_batch) for the device-resident arm
     sess = coverm_b200.Session(device=local_rank, threads=threads)
+    single_out = None
+    if strong:
+        if rank == 0:  # the single-GPU answer for the same file, before the group forms: the sharded run must print the same text
+            r1 = sess.run(argv, memory_inputs={bam: bam_bytes})
+            if r1.status != 0:
+                raise SystemExit(f"coverm_b200 failed: {r1.err}")
+            single_out = r1.out
+        idt = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            idt.copy_(torch.frombuffer(bytearray(coverm_b200.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(idt, 0)
+        sess.set_group(rank, world, nccl_id=bytes(idt.cpu().numpy()))
+
+    # ---------------------------------------------------------------- one e2e pass: warms the session and leaves this rank's
+    # tuples in HBM (cmb_last_bgzf_batch) for the device-resident arm
     res = sess.run(argv, memory_inputs={bam: bam_bytes})
     if res.status != 0:
         raise SystemExit(f"coverm_b200 failed: {res.err}")
-    if not res.samples[0]["device_decode"]:
+    s_first = res.samples[0]
+    if not s_first["device_decode"]:
         raise SystemExit("the device-side decoder declined the bench file; the device-resident arm needs its tuples in HBM")
     n_contigs = args.contigs
     ctx = sess.device_context()
     ctx.n_contigs = n_contigs
     batch, n_rec, n_iv = ctx.last_bgzf_batch()
-    assert n_rec == res.samples[0]["n_records"], (n_rec, res.samples[0]["n_records"])
-    log(f"rank {rank}: {n_rec} records, {n_iv} interval slots resident in HBM")
+    log(f"rank {rank}: {n_rec} records, {n_iv} interval slots resident in HBM; contigs [{s_first['tid_begin']}, {s_first['tid_end']}), "
+        f"{s_first['shard_blocks']} of {s_first['total_blocks']} BGZF blocks")
+    cuts = None
+    if strong:
+        t = torch.tensor([s_first["tid_begin"]], dtype=torch.int64, device="cuda")
+        allb = [torch.zeros_like(t) for _ in range(world)]
+        dist.all_gather(allb, t)
+        cuts = [int(x.item()) for x in allb] + [n_contigs]
 
     # ---------------------------------------------------------------- device arm: tuples resident in HBM
     stream = torch.cuda.ExternalStream(ctx.stream())
     row_bytes = n_contigs * C_sizeof(ContigStats)
-    # N > 1: the single collective of the path is the all-gather of the per-contig table over NVLink.  The rows are
-    # snapshotted on the ctx stream (the next sample re-zeroes them) and gathered from the snapshot on NCCL's stream while
-    # the next sample's kernels run; two snapshot/gather buffers, and every gather is waited for inside the timed region.
-    gathered = [torch.empty(world * row_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
-    snap = [torch.empty(row_bytes, dtype=torch.uint8, device="cuda") for _ in range(2)] if world > 1 else None
-    pending = [None, None]
-    step_no = [0]
-    row_views = {}
 
     def device_step():
         ctx.begin_sample()
         ctx.submit_device_batch(batch, n_rec, n_iv)
-        ptr = ctx.end_sample_device()  # K1c/K1b/K2/K3 + error check (stream-synchronous)
-        if world > 1:
-            k = step_no[0] & 1
-            step_no[0] += 1
-            with torch.cuda.stream(stream):
-                if pending[k] is not None:
-                    pending[k].wait()  # the gather that last used this buffer pair (two samples ago)
-                if ptr not in row_views:  # the library's row table lives at a fixed address between set_reference calls
-                    row_views[ptr] = _device_view(ptr, row_bytes, local_rank)
-                snap[k].copy_(row_views[ptr], non_blocking=True)
-                pending[k] = dist.all_gather_into_tensor(gathered[k], snap[k], async_op=True)
-        return ptr
-
-    def drain_gathers():
-        for k in (0, 1):
-            if pending[k] is not None:
-                pending[k].wait()
-                pending[k] = None
-        torch.cuda.synchronize()
+        ctx.end_sample_device()  # K1c/K1b/K2/K3 + error check (stream-synchronous)
+        if strong:
+            ctx.allgather_stats(cuts)  # the collective of the path, on the same stream (NCCL broadcasts of each rank's row range)
 
     sampler = ClockSampler(local_rank)
     n_warm = max(3, args.warmup)
     for _ in range(n_warm):
         device_step()
-    drain_gathers()
+    torch.cuda.synchronize()
     barrier()
     sampler.start()
     k2_ms, k1_ms, k3_ms, k0_ms, dev_ms = [], [], [], [], []
@@ -357,18 +365,12 @@ def main():
         launches += tm["k1_launches"] + 3 + tm["k2_launches"] + tm["k3_launches"]  # K1 per batch, K1c, K1b x2, K2, K3
     with torch.cuda.stream(stream):
         ev1.record()
-    drain_gathers()
+    torch.cuda.synchronize()
     wall_ms = (time.perf_counter() - t_wall) * 1e3
-    if world > 1:  # the gathered table holds this rank's rows where they belong
-        k_last = (step_no[0] - 1) & 1
-        mine = gathered[k_last][rank * row_bytes:(rank + 1) * row_bytes]
-        if not torch.equal(mine, snap[k_last]):
-            raise SystemExit(f"rank {rank}: all-gathered table does not contain this rank's rows")
     barrier()
-    event_ms = ev0.elapsed_time(ev1)
-    # N > 1: the gathers run on NCCL's stream and are drained before the clock stops: use the wall clock then
-    step_ms = max_over_ranks((wall_ms if world > 1 else event_ms) / args.steps)
-    total_reads = sum_over_ranks(float(n_rec))
+    event_ms = ev0.elapsed_time(ev1)  # the gather is enqueued on the same stream: the events bracket it too
+    step_ms = max_over_ranks(event_ms / args.steps)
+    total_reads = float(file_records) if strong else sum_over_ranks(float(n_rec))
     value = total_reads / (step_ms * 1e-3)
     arena_elems = ctx.timing()["arena_elems"]
     mean = lambda v: sum(v) / len(v)
@@ -378,7 +380,7 @@ def main():
     achieved = algo_bytes / (k2_mean * 1e-3) / 1e9
     traffic, traffic_src = None, None
     tpath = os.path.join(ROOT, "profiles", "k2_traffic.json")
-    if os.path.exists(tpath) and args.config == "2":
+    if os.path.exists(tpath) and args.config == "2" and world == 1:
         tj = json.load(open(tpath))
         traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source", "profiles/k2_traffic.json (ncu --set full capture of this workload)")
 
@@ -406,26 +408,36 @@ def main():
     sampler.join(timeout=2)
     s0 = breakdown[-1]
     e2e_value = total_reads / e2e_s
-    h2d = s0["h2d_bytes"]  # device decode: the BGZF bytes + block table; host decode: 40 B/record + 8 B/interval tuples
-    d2h = row_bytes
+    # device decode: the BGZF bytes of the rank's block range + block table; host decode: 40 B/record + 8 B/interval tuples
+    h2d = sum_over_ranks(float(s0["h2d_bytes"]))
+    d2h = row_bytes * world
     e2e_launches = s0["decode_launches"] + s0["k1_launches"] + 3 + s0["k2_launches"] + s0["k3_launches"]
     e2e_out = res.out  # the table of the last timed step (full file)
+    same_as_single = None
+    if strong and rank == 0:
+        same_as_single = e2e_out == single_out
+        if not same_as_single:
+            log("MISMATCH: the sharded run's table differs from the single-GPU run of the same file")
 
     # ---------------------------------------------------------------- cold CLI: one fresh process on the same file
     cold = None
-    if rank == 0 and world == 1 and not args.skip_cold_cli:
+    if rank == 0 and not args.skip_cold_cli:
         out_path = os.path.join(args.workdir, "cold_cli.tsv")
+        extra = ["--gpus", str(world)] if strong else []
         t_c = time.perf_counter()
-        p = subprocess.run([coverm_b200.COVERM_BIN] + argv + ["-o", out_path], capture_output=True, text=True)
+        p = subprocess.run([coverm_b200.COVERM_BIN] + coverm_argv(cfg, bam, ncpu if strong else threads) + extra + ["-o", out_path],
+                           capture_output=True, text=True) if (world == 1 or strong) else None
         cold_s = time.perf_counter() - t_c
-        same = p.returncode == 0 and open(out_path).read() == e2e_out
-        cold = {"seconds": cold_s, "reads_per_s": n_rec / cold_s, "output_identical_to_session_run": same,
-                "what": "one fresh `bin/coverm` process, file read from the page cache: CUDA context + arena cudaMalloc + "
-                        "tensor-map encode + header parse + decode + kernels + printing to a file"}
-        if not same:
-            log(f"cold CLI run differs or failed (rc {p.returncode}): {p.stderr[-400:]}")
+        if p is not None:
+            same = p.returncode == 0 and open(out_path).read() == e2e_out
+            cold = {"seconds": cold_s, "reads_per_s": file_records / cold_s, "output_identical_to_session_run": same,
+                    "what": "one fresh `bin/coverm" + (f" --gpus {world}" if strong else "") + "` process, file read from the page cache: CUDA "
+                            "context(s) + arena cudaMalloc + tensor-map encode + header parse + decode + kernels + printing to a file"}
+            if not same:
+                log(f"cold CLI run differs or failed (rc {p.returncode}): {p.stderr[-400:]}")
+    barrier()
 
-    # ---------------------------------------------------------------- CPU baseline + parity on the FULL file
+    # ---------------------------------------------------------------- CPU baseline + parity on the FULL file (N = 1 only)
     cpu = None
     parity = None
     if rank == 0 and world == 1 and not args.skip_cpu_baseline:
@@ -439,29 +451,35 @@ def main():
     sess.close()
 
     if rank == 0:
-        config = workload_config(cfg, args, info, world, "weak")
-        host = {"host_threads_per_rank": threads, "host_cpus_effective": ncpu, "host_cpus_visible": os.cpu_count(), "reads_per_gpu": n_rec}
+        scaling = "strong" if strong else "weak"
+        config = workload_config(cfg, args, info, world, scaling)
+        host = {"host_threads_per_rank": threads, "host_cpus_effective": ncpu, "host_cpus_visible": os.cpu_count(), "records_rank0": n_rec}
         line = {
             "metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps, "warmup": n_warm,
-            "ms_per_step": step_ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "i32",
+            "ms_per_step": step_ms, "higher_is_better": True, "scaling": scaling, "vs_baseline": None, "dtype": "i32",
             "data": "synthetic", "config": config, "host": host, "clocks": sampler.summary(),
             "e2e": {"value": e2e_value, "unit": "reads/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
                     "seconds_per_step": e2e_s, "steps": e2e_steps,
-                    "breakdown_last_step": {k: s0[k] for k in ["total_s", "decode_s", "submit_wait_s", "end_sample_s", "k0_ms", "k1_ms",
-                                                               "k2_ms", "k3_ms", "device_total_ms", "device_decode",
-                                                               "decode_host_blocks", "decode_copy_inflate_ms", "decode_chain_ms",
-                                                               "decode_extract_ms"]},
+                    "breakdown_last_step_rank0": {k: s0[k] for k in ["total_s", "decode_s", "submit_wait_s", "end_sample_s", "gather_s", "k0_ms", "k1_ms",
+                                                                     "k2_ms", "k3_ms", "device_total_ms", "device_decode",
+                                                                     "decode_host_blocks", "decode_copy_inflate_ms", "decode_chain_ms",
+                                                                     "decode_extract_ms", "shard_blocks", "total_blocks", "range_probes",
+                                                                     "tid_begin", "tid_end", "group_ranks"]},
                     "step_walls_s": step_walls, "gpu_launches_per_step": int(e2e_launches),
                     "decode": "device (kd_inflate_g8/kd_guess/kd_walk/kd_extract: compressed BGZF bytes cross PCIe)" if s0["device_decode"] else "host pipeline (tuples cross PCIe)",
                     "input": f"BAM bytes ({len(bam_bytes)} B) in pinned host memory, cmbh_run (== `coverm {cfg['sub']}`), TSV text out; "
-                             "warm session (context, arena, decode buffers and the parsed header are reused across steps)",
+                             "warm session (context, arena, decode buffers and the parsed header are reused across steps)" +
+                             ("; collective: every rank calls cmbh_run, the in-library NCCL gather is inside the timed region" if strong else ""),
+                    "output_identical_to_single_gpu_run": same_as_single,
                     "cold_cli": cold},
             "gpu_launches": int(launches),
             "roofline": {"bound": "hbm", "kernel": "k2_scan_reduce<HIST,CLEAN>", "achieved": achieved, "peak": peak, "unit": "GB/s",
                          "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": k2_mean},
-            "device_breakdown_ms": {"k0_zero": mean(k0_ms), "k1_filter_delta+carry": mean(k1_ms), "k2_scan_reduce": k2_mean,
-                                    "k3_finalize": mean(k3_ms), "stream_total": mean(dev_ms), "wall_per_step": wall_ms / args.steps},
+                         "algorithmic_bytes_per_launch": algo_bytes, "avg_launch_ms": k2_mean,
+                         "note": "rank 0's launch" + (" (1/N of the arena)" if strong else "")},
+            "device_breakdown_ms_rank0": {"k0_zero": mean(k0_ms), "k1_filter_delta+carry": mean(k1_ms), "k2_scan_reduce": k2_mean,
+                                          "k3_finalize": mean(k3_ms), "kernels_stream_total": mean(dev_ms), "step_incl_gather": event_ms / args.steps,
+                                          "wall_per_step": wall_ms / args.steps},
             "cpu_baseline": cpu, "parity": parity,
             "parity_what": "text of the e2e table of the full file == oracle/coverm_oracle's output of the same file" if parity is not None else None,
         }
@@ -473,18 +491,6 @@ def main():
 def C_sizeof(t):
     import ctypes
     return ctypes.sizeof(t)
-
-
-def _device_view(ptr, nbytes, device_index):
-    """A torch uint8 tensor aliasing `nbytes` of device memory at `ptr` (the library's per-contig row table)."""
-    import torch
-
-    class _Holder:
-        pass
-
-    h = _Holder()
-    h.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1", "data": (int(ptr), False), "version": 3}
-    return torch.as_tensor(h, device=torch.device("cuda", device_index))
 
 
 if __name__ == "__main__":

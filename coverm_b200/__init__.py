@@ -79,7 +79,9 @@ class SampleInfo(C.Structure):
                 ("k2_launches", C.c_uint32), ("k3_launches", C.c_uint32), ("arena_elems", C.c_uint64),
                 ("n_intervals", C.c_uint64), ("h2d_bytes", C.c_uint64), ("device_decode", C.c_uint32),
                 ("decode_host_blocks", C.c_uint32), ("decode_copy_inflate_ms", C.c_float), ("decode_chain_ms", C.c_float),
-                ("decode_extract_ms", C.c_float), ("decode_launches", C.c_uint32)]
+                ("decode_extract_ms", C.c_float), ("decode_launches", C.c_uint32), ("group_ranks", C.c_uint32),
+                ("shard_blocks", C.c_uint32), ("total_blocks", C.c_uint32), ("range_probes", C.c_uint32), ("tid_begin", C.c_uint32), ("tid_end", C.c_uint32), ("reserved", C.c_uint32),
+                ("gather_s", C.c_double)]
 
 
 class HostResult(C.Structure):
@@ -89,7 +91,8 @@ class HostResult(C.Structure):
 
 DEVICE_SYMBOLS = ["cmb_abi_version", "cmb_create", "cmb_destroy", "cmb_last_error", "cmb_set_reference",
                   "cmb_set_params", "cmb_begin_sample", "cmb_acquire_batch", "cmb_submit_batch",
-                  "cmb_submit_device_batch", "cmb_submit_bgzf", "cmb_last_bgzf_batch", "cmb_end_sample", "cmb_fetch_pairs", "cmb_end_sample_device",
+                  "cmb_submit_device_batch", "cmb_submit_bgzf", "cmb_last_bgzf_batch", "cmb_end_sample", "cmb_comm_unique_id",
+                  "cmb_comm_init", "cmb_comm_init_local", "cmb_comm_destroy", "cmb_comm_allgather", "cmb_allgather_stats", "cmb_kept_tid_range", "cmb_fetch_pairs", "cmb_end_sample_device",
                   "cmb_get_timing", "cmb_stream", "cmb_host_alloc", "cmb_host_free"]
 class Tuples(C.Structure):
     _fields_ = [("n_contigs", C.c_uint32), ("contig_len", C.POINTER(C.c_uint64)), ("n_records", C.c_uint64),
@@ -100,7 +103,7 @@ class Tuples(C.Structure):
                 ("iv_start", C.POINTER(C.c_int32)), ("iv_len", C.POINTER(C.c_int32))]
 
 
-HOST_SYMBOLS = ["cmbh_session_create", "cmbh_session_destroy", "cmbh_last_error", "cmbh_session_set_shard", "cmbh_session_ctx",
+HOST_SYMBOLS = ["cmbh_session_create", "cmbh_session_destroy", "cmbh_last_error", "cmbh_session_set_shard", "cmbh_session_set_group", "cmbh_session_ctx",
                 "cmbh_run", "cmbh_plan_params", "cmbh_free_result", "cmbh_main", "cmbh_extract_tuples", "cmbh_free_tuples"]
 
 
@@ -121,6 +124,18 @@ def extract_tuples(path, threads=None):
     return out
 
 _lib = None
+
+
+ALLGATHER_FN = C.CFUNCTYPE(C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p)
+
+
+def comm_unique_id():
+    """128 bytes identifying a new NCCL communicator (cmb_comm_unique_id); rank 0 creates it and shares it."""
+    lib = load_library()
+    buf = (C.c_uint8 * 128)()
+    if lib.cmb_comm_unique_id(buf) != 0:
+        raise CmbError("cmb_comm_unique_id failed: " + lib.cmb_last_error(None).decode())
+    return bytes(buf)
 
 
 def plan_params(argv):
@@ -170,6 +185,9 @@ def load_library(path=None):
     lib.cmbh_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(MemInput), C.c_int,
                              C.POINTER(HostResult)]
     lib.cmb_last_bgzf_batch.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.cmbh_session_set_group.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.cmb_comm_unique_id.argtypes = [C.c_void_p]
+    lib.cmb_allgather_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
     lib.cmbh_session_ctx.argtypes = [C.c_void_p]
     lib.cmbh_session_ctx.restype = C.c_void_p
     lib.cmbh_plan_params.argtypes = [C.c_int, C.POINTER(C.c_char_p), C.c_void_p]
@@ -227,6 +245,29 @@ class Session:
 
     def set_shard(self, tid_begin, tid_end):
         self._lib.cmbh_session_set_shard(self._h, tid_begin, tid_end)
+
+    def set_group(self, rank, n_ranks, nccl_id=None, allgather=None):
+        """Make this session rank `rank` of `n_ranks` processing every sample together (contig sharding).  `nccl_id`: the 128
+        bytes of comm_unique_id() shared by the caller; or `allgather(send: bytes, n_ranks) -> bytes` (the ranks' buffers
+        concatenated in rank order) for hosts without NCCL between them."""
+        cb = None
+        if allgather is not None:
+            def _cb(user, send, nbytes, recv):
+                try:
+                    out = allgather(C.string_at(send, nbytes))
+                    C.memmove(recv, out, nbytes * n_ranks)
+                    return 0
+                except Exception:
+                    import traceback
+                    traceback.print_exc()
+                    return 1
+            cb = ALLGATHER_FN(_cb)
+        self._group_cb = cb  # keep the trampoline alive
+        idbuf = (C.c_uint8 * 128).from_buffer_copy(nccl_id) if nccl_id is not None else None
+        rc = self._lib.cmbh_session_set_group(self._h, int(rank), int(n_ranks), C.cast(idbuf, C.c_void_p) if idbuf is not None else None,
+                                              C.cast(cb, C.c_void_p) if cb is not None else None, None)
+        if rc != 0:
+            raise CmbError("cmbh_session_set_group failed: " + self._lib.cmbh_last_error().decode())
 
     def device_context(self):
         """The session's cmb_ctx as a (borrowed) DeviceContext: continue on the device ABI after run()."""
@@ -334,6 +375,11 @@ class DeviceContext:
         p = C.c_void_p()
         self._check(self._lib.cmb_end_sample_device(self._h, C.byref(p)), "cmb_end_sample_device")
         return p.value
+
+    def allgather_stats(self, tid_cuts):
+        """cmb_allgather_stats without host copies: completes the per-contig table on every rank's device (collective)."""
+        cuts = (C.c_uint32 * len(tid_cuts))(*tid_cuts)
+        self._check(self._lib.cmb_allgather_stats(self._h, cuts, None, None, None), "cmb_allgather_stats")
 
     def end_sample(self):
         import numpy as np

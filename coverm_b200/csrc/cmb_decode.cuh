@@ -665,13 +665,18 @@ struct ExtractArgs {
   int32_t* iv_len;
   unsigned long long* n_primary;
   uint32_t* flags;
+  // counters cover the records this call OWNS: own_lo <= tid < own_hi, plus tid < 0 when own_unplaced (multi-GPU: the walks
+  // of neighbouring ranks overlap by a block; each record is counted by exactly one rank)
+  int32_t own_lo, own_hi;
+  uint32_t own_unplaced;
+  unsigned long long* n_owned;
 };
 
 __global__ void __launch_bounds__(256) kd_extract(const ExtractArgs a) {
   const uint64_t i = (uint64_t)blockIdx.x * 256 + threadIdx.x;
   const bool valid = i < a.n_records;
   uint32_t err = 0;
-  bool primary = false;
+  bool primary = false, owned = false;
   if (valid) {
     const uint8_t* rec = a.data + a.rec_off[i];
     const uint32_t block_size = ldu32(rec);
@@ -685,7 +690,8 @@ __global__ void __launch_bounds__(256) kd_extract(const ExtractArgs a) {
     a.flag[i] = (uint16_t)flag;
     a.mapq[i] = (uint8_t)mapq;
     a.l_seq[i] = l_seq;
-    primary = !(flag & 0x900);
+    owned = tid < 0 ? a.own_unplaced != 0 : (tid >= a.own_lo && tid < a.own_hi);
+    primary = owned && !(flag & 0x900);
     const uint8_t* cig = o + 32 + l_read_name;
     const uint8_t* aux = cig + 4ull * n_cigar + (l_seq + 1) / 2 + l_seq;
     uint32_t iv = a.iv_begin[i];
@@ -767,8 +773,9 @@ __global__ void __launch_bounds__(256) kd_extract(const ExtractArgs a) {
     a.nm_state[i] = (uint8_t)nm_state;
     a.nm[i] = nm;
   }
-  const uint32_t np = __popc(__ballot_sync(FULL, primary));
+  const uint32_t np = __popc(__ballot_sync(FULL, primary)), no = __popc(__ballot_sync(FULL, owned));
   if ((threadIdx.x & 31) == 0 && np) atomicAdd(a.n_primary, (unsigned long long)np);
+  if ((threadIdx.x & 31) == 0 && no) atomicAdd(a.n_owned, (unsigned long long)no);
   err = __reduce_or_sync(FULL, err);
   if (err && (threadIdx.x & 31) == 0) atomicOr(a.flags, err);
 }

@@ -40,6 +40,7 @@
 #include <thread>
 #include <vector>
 
+#include <nccl.h>
 #include <zlib.h>
 
 #include "../../include/coverm_b200.h"
@@ -52,6 +53,12 @@ namespace {
 #include "cmb_k3.cuh"
 #include "cmb_decode.cuh"
 #include "cmb_decode_g8.cuh"
+
+// rows[i].hist_offset += base for the rows that carry histogram pairs (cmb_allgather_stats: local -> global pair offsets)
+__global__ void __launch_bounds__(256) k_rebase_hist_offsets(cmb_contig_stats* rows, uint32_t n, uint64_t base) {
+  const uint32_t i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n && rows[i].hist_count) rows[i].hist_offset += base;
+}
 
 // ------------------------------------------------------------------------------------------------ host context
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -90,7 +97,16 @@ struct cmb_ctx {
   int32_t *d_tail_sum = nullptr, *d_carry_in = nullptr;
   int2* d_block_agg = nullptr;
   cmb_contig_stats* d_rows = nullptr;
-  uint32_t* d_counters = nullptr;  // [0] error flags, [1] ticket, [2] rec_count, [3] ovf_count, [4..5] pair_count (u64)
+  uint32_t* d_counters = nullptr;  // [0] error flags, [1] ticket, [2] rec_count, [3] ovf_count, [4..5] pair_count (u64),
+                                   // [6..7] kept tid range of the exclusive records (K1Args::kept_range)
+  uint32_t kept_range[2] = {0, 0};  // host copy after cmb_end_sample*
+  // multi-GPU (cmb_comm_*): one NCCL communicator per ctx, collectives on the ctx stream
+  ncclComm_t comm = nullptr;
+  int comm_rank = 0, comm_size = 1;
+  uint8_t* d_xchg = nullptr;  // staging of cmb_comm_allgather
+  size_t xchg_cap = 0;
+  cmb_hist_pair* d_pairs_all = nullptr;  // concatenated histogram pairs of all ranks (cmb_allgather_stats)
+  uint64_t pairs_all_capacity = 0;
   uint2* d_rec = nullptr;
   uint32_t rec_capacity = 0;
   uint2* d_warp_table = nullptr;
@@ -235,7 +251,7 @@ void free_reference(cmb_ctx* c) {
   c->pair_capacity = 0;
 }
 
-int launch_k1(cmb_ctx* c, const cmb_read_batch& b, uint32_t n_records, uint32_t n_intervals) {
+int launch_k1(cmb_ctx* c, const cmb_read_batch& b, uint32_t n_records, uint32_t n_intervals, uint32_t excl_n = 0xffffffffu) {
   if (n_records == 0) return CMB_OK;
   const uint32_t blocks = (n_records + K1_THREADS - 1) / K1_THREADS;
   if (c->block_minmax_used + blocks > c->block_minmax_capacity) {
@@ -260,6 +276,8 @@ int launch_k1(cmb_ctx* c, const cmb_read_batch& b, uint32_t n_records, uint32_t 
   a.arena = c->d_arena; a.tail_sum = c->d_tail_sum; a.rows = c->d_rows;
   a.block_minmax = c->d_block_minmax + c->block_minmax_used;
   a.error_flags = c->d_counters + 0;
+  a.kept_range = c->d_counters + 6;
+  a.excl_n = excl_n;
   a.p = c->params;
   a.filter_single = c->mode.filter_single_reads;
   a.filter_pairs = c->mode.filter_pairs;
@@ -346,11 +364,13 @@ int run_end_of_sample(cmb_ctx* c) {
 }
 
 int collect_errors_and_timing(cmb_ctx* c, uint32_t* counters_out) {
-  uint32_t h[6];
+  uint32_t h[8];
   CU_TRY(c, cudaMemcpyAsync(h, c->d_counters, sizeof h, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaEventRecord(c->ev[6], c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
-  memcpy(counters_out, h, sizeof h);
+  memcpy(counters_out, h, 6 * sizeof(uint32_t));
+  c->kept_range[0] = h[6];
+  c->kept_range[1] = h[7];
   float ms = 0;
   cudaEventElapsedTime(&ms, c->ev[0], c->ev[1]); c->timing.ms_zero = ms;
   cudaEventElapsedTime(&ms, c->ev[3], c->ev[4]); c->timing.ms_scan = ms;
@@ -469,6 +489,9 @@ void cmb_destroy(cmb_ctx* c) {
     if (e) cudaEventDestroy(e);
   cudaFree(c->d_counters);
   cudaFree(c->d_block_minmax);
+  cmb_comm_destroy(c);
+  cudaFree(c->d_xchg);
+  cudaFree(c->d_pairs_all);
   {
     auto& d = c->dec;
     cudaFree(d.d_comp); cudaFree(d.d_inflated); cudaFree(d.d_coff); cudaFree(d.d_ustart); cudaFree(d.d_guess); cudaFree(d.d_exit);
@@ -686,10 +709,10 @@ int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** dev_stats) {
 }
 
 int cmb_end_sample(cmb_ctx* c, cmb_contig_stats* stats, cmb_hist_pair* pairs, uint64_t pairs_capacity, uint64_t* n_pairs) {
-  if (!c || !stats) return fail(c, CMB_E_ARG, "cmb_end_sample: null argument");
+  if (!c) return fail(c, CMB_E_ARG, "cmb_end_sample: null argument");
   int rc = cmb_end_sample_device(c, nullptr);
   if (rc) return rc;
-  CU_TRY(c, cudaMemcpyAsync(stats, c->d_rows, sizeof(cmb_contig_stats) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost, c->stream));
+  if (stats) CU_TRY(c, cudaMemcpyAsync(stats, c->d_rows, sizeof(cmb_contig_stats) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost, c->stream));
   uint64_t np = 0;
   if ((c->params.want & CMB_WANT_HIST_CSR) && c->n_local) {
     unsigned long long cnt = 0;
@@ -727,6 +750,146 @@ int cmb_get_timing(const cmb_ctx* c, cmb_sample_timing* out) {
 
 void* cmb_stream(cmb_ctx* c) { return c ? (void*)c->stream : nullptr; }
 
+// ------------------------------------------------------------------------------------------------ multi-GPU (NCCL)
+#define NCCL_TRY(ctx, expr)                                                                                       \
+  do {                                                                                                            \
+    ncclResult_t r_ = (expr);                                                                                     \
+    if (r_ != ncclSuccess) return fail(ctx, CMB_E_CUDA, "%s failed: %s (%s:%d)", #expr, ncclGetErrorString(r_), __FILE__, __LINE__); \
+  } while (0)
+
+int cmb_comm_unique_id(uint8_t id[CMB_COMM_ID_BYTES]) {
+  static_assert(sizeof(ncclUniqueId) == CMB_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
+  if (!id) return fail(nullptr, CMB_E_ARG, "cmb_comm_unique_id: null argument");
+  ncclUniqueId u;
+  NCCL_TRY(nullptr, ncclGetUniqueId(&u));
+  memcpy(id, &u, sizeof u);
+  return CMB_OK;
+}
+
+int cmb_comm_init(cmb_ctx* c, const uint8_t id[CMB_COMM_ID_BYTES], int rank, int n_ranks) {
+  if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(c, CMB_E_ARG, "cmb_comm_init: bad arguments");
+  if (c->comm) return fail(c, CMB_E_ARG, "cmb_comm_init: the context already has a communicator");
+  CU_TRY(c, cudaSetDevice(c->device));
+  ncclUniqueId u;
+  memcpy(&u, id, sizeof u);
+  NCCL_TRY(c, ncclCommInitRank(&c->comm, n_ranks, u, rank));
+  c->comm_rank = rank;
+  c->comm_size = n_ranks;
+  return CMB_OK;
+}
+
+int cmb_comm_init_local(cmb_ctx* const* ctxs, int n_ranks) {
+  if (!ctxs || n_ranks < 1) return fail(nullptr, CMB_E_ARG, "cmb_comm_init_local: bad arguments");
+  std::vector<int> devs(n_ranks);
+  for (int r = 0; r < n_ranks; ++r) {
+    if (!ctxs[r] || ctxs[r]->comm) return fail(ctxs[r], CMB_E_ARG, "cmb_comm_init_local: null context or communicator already set");
+    devs[r] = ctxs[r]->device;
+  }
+  std::vector<ncclComm_t> comms(n_ranks);
+  NCCL_TRY(ctxs[0], ncclCommInitAll(comms.data(), n_ranks, devs.data()));
+  for (int r = 0; r < n_ranks; ++r) {
+    ctxs[r]->comm = comms[r];
+    ctxs[r]->comm_rank = r;
+    ctxs[r]->comm_size = n_ranks;
+  }
+  return CMB_OK;
+}
+
+void cmb_comm_destroy(cmb_ctx* c) {
+  if (!c || !c->comm) return;
+  cudaSetDevice(c->device);
+  if (c->stream) cudaStreamSynchronize(c->stream);
+  ncclCommDestroy(c->comm);
+  c->comm = nullptr;
+  c->comm_rank = 0;
+  c->comm_size = 1;
+}
+
+int cmb_comm_allgather(cmb_ctx* c, const void* send, void* recv, size_t bytes) {
+  if (!c || !send || !recv || !bytes) return fail(c, CMB_E_ARG, "cmb_comm_allgather: bad arguments");
+  if (!c->comm) return fail(c, CMB_E_ARG, "cmb_comm_allgather: no communicator (cmb_comm_init first)");
+  CU_TRY(c, cudaSetDevice(c->device));
+  const size_t need = bytes * (size_t)(c->comm_size + 1);
+  if (c->xchg_cap < need) {
+    cudaFree(c->d_xchg);
+    c->d_xchg = nullptr;
+    c->xchg_cap = 0;
+    CU_TRY(c, cudaMalloc(&c->d_xchg, need + 4096));
+    c->xchg_cap = need + 4096;
+  }
+  uint8_t* d_send = c->d_xchg;
+  uint8_t* d_recv = c->d_xchg + bytes;
+  CU_TRY(c, cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, c->stream));
+  NCCL_TRY(c, ncclAllGather(d_send, d_recv, bytes, ncclChar, c->comm, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(recv, d_recv, bytes * (size_t)c->comm_size, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return CMB_OK;
+}
+
+int cmb_allgather_stats(cmb_ctx* c, const uint32_t* tid_cuts, const uint64_t* pair_base, cmb_contig_stats* stats, cmb_hist_pair* pairs) {
+  if (!c || !tid_cuts) return fail(c, CMB_E_ARG, "cmb_allgather_stats: null argument");
+  if (!c->comm) return fail(c, CMB_E_ARG, "cmb_allgather_stats: no communicator (cmb_comm_init first)");
+  if (!c->ended || !c->d_rows) return fail(c, CMB_E_ARG, "cmb_allgather_stats: no ended sample");
+  const int N = c->comm_size, me = c->comm_rank;
+  if (tid_cuts[0] != 0 || tid_cuts[N] != c->n_contigs || tid_cuts[me] != c->tid_begin || tid_cuts[me + 1] != c->tid_end)
+    return fail(c, CMB_E_ARG, "cmb_allgather_stats: tid_cuts do not match this context's shard");
+  for (int r = 0; r < N; ++r)
+    if (tid_cuts[r] > tid_cuts[r + 1]) return fail(c, CMB_E_ARG, "cmb_allgather_stats: tid_cuts must be non-decreasing");
+  CU_TRY(c, cudaSetDevice(c->device));
+  const bool csr = pair_base && (c->params.want & CMB_WANT_HIST_CSR);
+  if (csr) {
+    const uint64_t total = pair_base[N];
+    if (pair_base[me + 1] - pair_base[me] > c->pair_capacity) return fail(c, CMB_E_ARG, "cmb_allgather_stats: pair_base exceeds this rank's pairs");
+    if (c->pairs_all_capacity < total || !c->d_pairs_all) {
+      cudaFree(c->d_pairs_all);
+      c->d_pairs_all = nullptr;
+      c->pairs_all_capacity = 0;
+      const uint64_t want = total + total / 8 + 1024;
+      CU_TRY(c, cudaMalloc(&c->d_pairs_all, sizeof(cmb_hist_pair) * want));
+      c->pairs_all_capacity = want;
+    }
+    const uint32_t n_own = c->tid_end - c->tid_begin;
+    if (n_own && pair_base[me]) {
+      k_rebase_hist_offsets<<<(n_own + 255) / 256, 256, 0, c->stream>>>(c->d_rows + c->tid_begin, n_own, pair_base[me]);
+      CU_TRY(c, cudaGetLastError());
+    }
+  }
+  // every rank broadcasts its own row range in place: afterwards each rank's table is complete (an all-gather with ragged counts)
+  NCCL_TRY(c, ncclGroupStart());
+  for (int r = 0; r < N; ++r) {
+    const size_t n = (size_t)(tid_cuts[r + 1] - tid_cuts[r]) * sizeof(cmb_contig_stats);
+    if (!n) continue;
+    cmb_contig_stats* p = c->d_rows + tid_cuts[r];
+    NCCL_TRY(c, ncclBroadcast(p, p, n, ncclChar, r, c->comm, c->stream));
+  }
+  if (csr) {
+    for (int r = 0; r < N; ++r) {
+      const size_t n = (size_t)(pair_base[r + 1] - pair_base[r]) * sizeof(cmb_hist_pair);
+      if (!n) continue;
+      NCCL_TRY(c, ncclBroadcast(c->d_pairs, c->d_pairs_all + pair_base[r], n, ncclChar, r, c->comm, c->stream));
+    }
+  }
+  NCCL_TRY(c, ncclGroupEnd());
+  if (stats) CU_TRY(c, cudaMemcpyAsync(stats, c->d_rows, sizeof(cmb_contig_stats) * (size_t)c->n_contigs, cudaMemcpyDeviceToHost, c->stream));
+  if (csr && pairs && pair_base[N])
+    CU_TRY(c, cudaMemcpyAsync(pairs, c->d_pairs_all, sizeof(cmb_hist_pair) * pair_base[N], cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return CMB_OK;
+}
+
+int cmb_kept_tid_range(cmb_ctx* c, int32_t* min_tid, int32_t* max_tid) {
+  if (!c || !min_tid || !max_tid) return fail(c, CMB_E_ARG, "cmb_kept_tid_range: null argument");
+  if (!c->ended) return fail(c, CMB_E_ARG, "cmb_kept_tid_range: no ended sample");
+  if (c->kept_range[0] == 0) {
+    *min_tid = INT_MAX;
+    *max_tid = INT_MIN;
+  } else {
+    *max_tid = (int32_t)(c->kept_range[0] - 1);
+    *min_tid = INT_MAX - (int32_t)c->kept_range[1];
+  }
+  return CMB_OK;
+}
+
 void* cmb_host_alloc(size_t bytes) {
   void* p = nullptr;
   if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) {
@@ -746,6 +909,8 @@ namespace {
 constexpr size_t DEC_COPY_CHUNK = 8u << 20;    // pinned staging slot
 constexpr size_t DEC_WINDOW_BYTES = 32u << 20; // compressed bytes per copy+inflate window
 constexpr size_t DEC_SLACK = 1024;
+constexpr size_t DEC_FRONT = 256;              // readable bytes in front of the first uploaded block (the bit readers align down)
+constexpr uint64_t DEC_TAIL_BYTES = 4u << 20;  // ranged decode: inflated bytes kept beyond the range for its last straddling record
 
 // Launch the inflate kernel over blocks [a.b0, a.b1): the four-streams-per-warp variant unless CMB_INFLATE_G8=0.
 int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool allow_g8 = true) {
@@ -825,18 +990,38 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     if (in->block_coffset[b] + in->block_clen[b] + 8 > in->size) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: block %u lies outside the data", b);
     ustart[b + 1] = ustart[b] + in->block_isize[b];
   }
-  const uint64_t total = ustart[nb];
-  if (in->records_at > total) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: records_at beyond the end of the stream");
-  if (in->records_at == total) return CMB_OK;  // header only
+  const uint64_t stream_total = ustart[nb];
+  if (in->records_at > stream_total) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: records_at beyond the end of the stream");
+  if (in->records_at == stream_total) return CMB_OK;  // header only
+  // Blocks: records starting in [first_block, walk_end) are decoded; [first_block, data_end) are uploaded and inflated (the tail
+  // beyond walk_end only supplies the bytes of a record that straddles out of the range).  Whole file: walk_end = data_end = nb.
   uint32_t first_block = (uint32_t)(std::upper_bound(ustart.begin(), ustart.end(), in->records_at) - ustart.begin()) - 1;
+  uint32_t walk_end = nb, data_end = nb;
+  if (in->ranged) {
+    if (in->walk_begin_block != first_block || in->walk_end_block > nb || in->walk_end_block < in->walk_begin_block)
+      return fail(c, CMB_E_ARG, "cmb_submit_bgzf: inconsistent block range");
+    walk_end = in->walk_end_block;
+    if (walk_end == first_block) return CMB_OK;  // an empty share
+    data_end = walk_end;
+    uint64_t tail = 0;
+    while (data_end < nb && tail < DEC_TAIL_BYTES) tail += in->block_isize[data_end++];
+  }
+  // Device buffers hold only [byte_lo, byte_hi) of the file and [u_lo, total) of the inflated stream; the kernels index both
+  // with absolute offsets through biased base pointers.
+  const uint64_t byte_lo = in->block_coffset[first_block];
+  const uint64_t byte_hi = data_end == nb ? in->size : in->block_coffset[data_end - 1] + in->block_clen[data_end - 1] + 8;
+  const uint64_t u_lo = ustart[first_block];
+  const uint64_t total = ustart[data_end];  // end of the inflated bytes available to this call
   // ---- buffers
   if (const char* lim = getenv("CMB_DECODE_MEM_LIMIT_MB")) {  // testing aid: behave as if the device had this much room
-    if ((in->size + total) >> 20 > strtoull(lim, nullptr, 10)) return CMB_E_NOMEM;
+    if (((byte_hi - byte_lo) + (total - u_lo)) >> 20 > strtoull(lim, nullptr, 10)) return CMB_E_NOMEM;
   }
   size_t dummy_cap;
   int rc;
-  if ((rc = dec_grow(c, d.d_comp, d.comp_cap, (size_t)in->size + DEC_SLACK))) return rc;
-  if ((rc = dec_grow(c, d.d_inflated, d.infl_cap, (size_t)total + DEC_SLACK))) return rc;
+  if ((rc = dec_grow(c, d.d_comp, d.comp_cap, (size_t)(byte_hi - byte_lo) + DEC_FRONT + DEC_SLACK))) return rc;
+  if ((rc = dec_grow(c, d.d_inflated, d.infl_cap, (size_t)(total - u_lo) + DEC_SLACK))) return rc;
+  uint8_t* const comp_base = reinterpret_cast<uint8_t*>(reinterpret_cast<uintptr_t>(d.d_comp) + DEC_FRONT - byte_lo);
+  uint8_t* const infl_base = reinterpret_cast<uint8_t*>(reinterpret_cast<uintptr_t>(d.d_inflated) - u_lo);
   if (d.blocks_cap < (size_t)nb + 1 || !d.d_coff) {
     const size_t want = (size_t)nb + nb / 8 + 64;
     cudaFree(d.d_coff); cudaFree(d.d_ustart); cudaFree(d.d_guess); cudaFree(d.d_exit); cudaFree(d.d_rec_base); cudaFree(d.d_cig_base);
@@ -860,16 +1045,16 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
   struct Window { uint32_t b0, b1; uint64_t byte0, byte1; };
   std::vector<Window> windows;
   {
-    uint32_t b = 0;
-    uint64_t byte0 = 0;
-    while (b < nb) {
+    uint32_t b = first_block;
+    uint64_t byte0 = byte_lo;
+    while (b < data_end) {
       uint32_t e = b;
       uint64_t byte1 = byte0;
-      while (e < nb && (e == b || in->block_coffset[e] + in->block_clen[e] + 8 - byte0 <= DEC_WINDOW_BYTES)) {
+      while (e < data_end && (e == b || in->block_coffset[e] + in->block_clen[e] + 8 - byte0 <= DEC_WINDOW_BYTES)) {
         byte1 = in->block_coffset[e] + in->block_clen[e] + 8;
         ++e;
       }
-      if (e == nb) byte1 = in->size;
+      if (e == data_end) byte1 = byte_hi;
       windows.push_back({b, e, byte0, byte1});
       b = e;
       byte0 = byte1;
@@ -888,7 +1073,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     CU_TRY(c, cudaHostAlloc((void**)&d.h_ones, 64, cudaHostAllocDefault));
     for (int k = 0; k < 16; ++k) d.h_ones[k] = 1;
   }
-  std::vector<uint32_t> block_window(nb);
+  std::vector<uint32_t> block_window(nb, 0);
   for (size_t w = 0; w < windows.size(); ++w)
     for (uint32_t b = windows[w].b0; b < windows[w].b1; ++b) block_window[b] = (uint32_t)w;
   // ---- copy threads, their streams and pinned slots
@@ -922,15 +1107,16 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
   CU_TRY(c, cudaMemsetAsync(d.d_status, 0, 4ull * nb, c->stream));
   CU_TRY(c, cudaMemcpyAsync(d.d_block_window, block_window.data(), 4ull * nb, cudaMemcpyHostToDevice, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * (windows.size() + 1), c->stream));
-  CU_TRY(c, cudaMemsetAsync(d.d_inflated + total, 0, DEC_SLACK, c->stream));
-  CU_TRY(c, cudaMemsetAsync(d.d_comp + in->size, 0, DEC_SLACK, c->stream));
+  CU_TRY(c, cudaMemsetAsync(infl_base + total, 0, DEC_SLACK, c->stream));
+  CU_TRY(c, cudaMemsetAsync(comp_base + byte_hi, 0, DEC_SLACK, c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.d_comp, 0, DEC_FRONT, c->stream));
   CU_TRY(c, cudaEventRecord(d.ev[1], c->stream));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(d.streams[t], d.ev[1], 0));
   {  // one persistent launch over every block; its warps wait for their block's window to arrive
     InflateArgs a{};
-    a.comp = d.d_comp; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
+    a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
     // blocks before the one holding the first record are header text the host has already read: not inflated here
-    a.b0 = first_block; a.b1 = nb; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
+    a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
     a.block_window = d.d_block_window; a.ready = d.d_tickets + 1;
     if ((rc = launch_inflate(c, a, c->stream))) return rc;
   }
@@ -953,14 +1139,14 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
       if (w >= windows.size() || first_err.load()) break;
       const Window& win = windows[w];
       if (src_pinned) {
-        if (!check(cudaMemcpyAsync(d.d_comp + win.byte0, in->data + win.byte0, win.byte1 - win.byte0, cudaMemcpyHostToDevice, st))) break;
+        if (!check(cudaMemcpyAsync(comp_base + win.byte0, in->data + win.byte0, win.byte1 - win.byte0, cudaMemcpyHostToDevice, st))) break;
       } else {
         for (uint64_t o = win.byte0; o < win.byte1; o += DEC_COPY_CHUNK) {
           const size_t n = (size_t)std::min<uint64_t>(DEC_COPY_CHUNK, win.byte1 - o);
           const size_t si = (size_t)t * 2 + slot;
           if (used[slot] && !check(cudaEventSynchronize(d.slot_events[si]))) return;
           memcpy(d.pinned[si], in->data + o, n);
-          if (!check(cudaMemcpyAsync(d.d_comp + o, d.pinned[si], n, cudaMemcpyHostToDevice, st))) return;
+          if (!check(cudaMemcpyAsync(comp_base + o, d.pinned[si], n, cudaMemcpyHostToDevice, st))) return;
           if (!check(cudaEventRecord(d.slot_events[si], st))) return;
           used[slot] = true;
           slot ^= 1;
@@ -985,7 +1171,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     cudaStreamSynchronize(c->stream);
   }
   out->n_launches = 1;
-  out->h2d_bytes = in->size + 24ull * nb + 8;
+  out->h2d_bytes = (byte_hi - byte_lo) + 24ull * nb + 8;
   if (first_err.load()) return fail(c, CMB_E_CUDA, "cmb_submit_bgzf: copy/inflate stage failed: %s", cudaGetErrorString((cudaError_t)first_err.load()));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(c->stream, d.done_events[t], 0));
   CU_TRY(c, cudaEventRecord(d.ev[2], c->stream));
@@ -996,16 +1182,16 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     cudaEventCreate(&p1);
     CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4, c->stream));
     InflateArgs a{};
-    a.comp = d.d_comp; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
-    a.b0 = first_block; a.b1 = nb; a.out = d.d_inflated; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 8;
+    a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
+    a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 8;
     cudaEventRecord(p0, c->stream);
     if ((rc = launch_inflate(c, a, c->stream))) return rc;
     cudaEventRecord(p1, c->stream);
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     float ms = 0;
     cudaEventElapsedTime(&ms, p0, p1);
-    fprintf(stderr, "#decode_profile\tinflate_only_ms=%.3f\tblocks=%u\tcompressed=%llu\tinflated=%llu\tinflated_GBps=%.2f\tcopy_threads=%u\tsrc_pinned=%d\tcopy_enqueue_wall_ms=%.2f\n", ms, nb,
-            (unsigned long long)in->size, (unsigned long long)total, total / ms * 1e-6, T, (int)src_pinned, copy_wall_ms);
+    fprintf(stderr, "#decode_profile\tinflate_only_ms=%.3f\tblocks=%u\tcompressed=%llu\tinflated=%llu\tinflated_GBps=%.2f\tcopy_threads=%u\tsrc_pinned=%d\tcopy_enqueue_wall_ms=%.2f\n", ms, data_end - first_block,
+            (unsigned long long)(byte_hi - byte_lo), (unsigned long long)(total - u_lo), (total - u_lo) / ms * 1e-6, T, (int)src_pinned, copy_wall_ms);
     cudaEventDestroy(p0);
     cudaEventDestroy(p1);
   }
@@ -1017,7 +1203,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     std::vector<uint32_t> status(nb);
     CU_TRY(c, cudaMemcpy(status.data(), d.d_status, 4ull * nb, cudaMemcpyDeviceToHost));
     if (getenv("CMB_DECODE_RETRY_TEST"))  // testing aid: pretend every 7th block was declined by the first pass (code 29)
-      for (uint32_t b = first_block; b < nb; b += 7) status[b] = 29;
+      for (uint32_t b = first_block; b < data_end; b += 7) status[b] = 29;
     if (getenv("CMB_DECODE_VERIFY")) {
       uint32_t hist[32] = {0};
       for (uint32_t b = 0; b < nb; ++b) hist[std::min<uint32_t>(status[b], 31)]++;
@@ -1030,7 +1216,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     // prefixes) than the four-streams-per-warp one, so most blocks the first pass declined for table space fit there.
     {
       std::vector<uint32_t> again;
-      for (uint32_t b = first_block; b < nb; ++b)
+      for (uint32_t b = first_block; b < data_end; ++b)
         if (status[b] != INF_OK) again.push_back(b);
       if (!again.empty()) {
         uint32_t* d_list = d.d_dirty;  // free until the record chain starts (nb entries)
@@ -1038,8 +1224,8 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
         CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4, c->stream));
         CU_TRY(c, cudaMemsetAsync(d.d_cnt, 0, 4, c->stream));
         InflateArgs a2{};
-        a2.comp = d.d_comp; a2.coff = d.d_coff; a2.clen = d.d_clen; a2.isize = d.d_isize; a2.uoff = d.d_ustart;
-        a2.b0 = 0; a2.b1 = (uint32_t)again.size(); a2.out = d.d_inflated; a2.status = d.d_status; a2.ticket = d.d_tickets;
+        a2.comp = comp_base; a2.coff = d.d_coff; a2.clen = d.d_clen; a2.isize = d.d_isize; a2.uoff = d.d_ustart;
+        a2.b0 = 0; a2.b1 = (uint32_t)again.size(); a2.out = infl_base; a2.status = d.d_status; a2.ticket = d.d_tickets;
         a2.fail_count = d.d_cnt + 0; a2.block_list = d_list;
         if ((rc = launch_inflate(c, a2, c->stream, false))) return rc;
         out->n_launches += 1;
@@ -1054,7 +1240,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     if (inflateInit2(&zs, -15) != Z_OK) return fail(c, CMB_E_NOMEM, "zlib init failed");
-    for (uint32_t b = 0; b < nb; ++b) {
+    for (uint32_t b = first_block; b < data_end; ++b) {
       if (status[b] == INF_OK) continue;
       const uint32_t isz = in->block_isize[b];
       if (tmp.size() < isz) tmp.resize(isz);
@@ -1069,19 +1255,19 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
         inflateEnd(&zs);
         return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: BGZF block %u does not inflate", b);
       }
-      CU_TRY(c, cudaMemcpy(d.d_inflated + ustart[b], tmp.data(), isz, cudaMemcpyHostToDevice));
+      CU_TRY(c, cudaMemcpy(infl_base + ustart[b], tmp.data(), isz, cudaMemcpyHostToDevice));
       out->n_blocks_host += 1;
     }
     inflateEnd(&zs);
   }
   if (getenv("CMB_DECODE_VERIFY")) {  // debugging aid: compare every device-inflated block with zlib's output
-    std::vector<uint8_t> dev(total), tmp(65536 + 64);
-    CU_TRY(c, cudaMemcpy(dev.data(), d.d_inflated, total, cudaMemcpyDeviceToHost));
+    std::vector<uint8_t> dev(total - u_lo), tmp(65536 + 64);
+    CU_TRY(c, cudaMemcpy(dev.data(), d.d_inflated, total - u_lo, cudaMemcpyDeviceToHost));
     z_stream zs;
     memset(&zs, 0, sizeof zs);
     inflateInit2(&zs, -15);
     uint32_t bad = 0;
-    for (uint32_t b = first_block; b < nb; ++b) {
+    for (uint32_t b = first_block; b < data_end; ++b) {
       const uint32_t isz = in->block_isize[b];
       if (!isz) continue;
       if (tmp.size() < isz) tmp.resize(isz);
@@ -1091,22 +1277,25 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
       zs.next_out = tmp.data();
       zs.avail_out = isz;
       const int zr = inflate(&zs, Z_FINISH);
-      if (zr != Z_STREAM_END || memcmp(tmp.data(), dev.data() + ustart[b], isz) != 0) {
+      if (zr != Z_STREAM_END || memcmp(tmp.data(), dev.data() + (ustart[b] - u_lo), isz) != 0) {
         uint32_t k = 0;
-        while (k < isz && tmp[k] == dev[ustart[b] + k]) ++k;
+        while (k < isz && tmp[k] == dev[ustart[b] - u_lo + k]) ++k;
         if (bad < 8) fprintf(stderr, "#decode_verify\tblock %u (clen %u isize %u): zlib rc %d, first difference at byte %u\n", b, in->block_clen[b], isz, zr, k);
         ++bad;
       }
     }
     inflateEnd(&zs);
-    fprintf(stderr, "#decode_verify\t%u of %u blocks differ from zlib; %u inflated on the host\n", bad, nb - first_block, out->n_blocks_host);
+    fprintf(stderr, "#decode_verify\t%u of %u blocks differ from zlib; %u inflated on the host\n", bad, data_end - first_block, out->n_blocks_host);
   }
   // ---- record chain
   WalkArgs wa{};
-  wa.data = d.d_inflated; wa.total = total; wa.ustart = d.d_ustart; wa.first_block = first_block; wa.n_blocks = nb;
+  // The chain is walked over [first_block, walk_hi): one block past the range when there is one, so that the range's last
+  // record boundary is also checked against an independent guess.
+  const uint32_t walk_hi = std::min<uint32_t>(walk_end + 1, data_end);
+  wa.data = infl_base; wa.total = total; wa.ustart = d.d_ustart; wa.first_block = first_block; wa.n_blocks = walk_hi;
   wa.records_at = in->records_at; wa.n_ref = (int32_t)in->n_ref; wa.guess = d.d_guess; wa.exit_off = d.d_exit; wa.n_rec = d.d_nrec;
   wa.n_cig = d.d_ncig; wa.dirty = d.d_dirty; wa.flags = d.d_cnt + 1; wa.only_dirty = 0;
-  const uint32_t nwb = nb - first_block;
+  const uint32_t nwb = walk_hi - first_block;
   CU_TRY(c, cudaMemsetAsync(d.d_dirty, 0, 4ull * nb, c->stream));
   kd_guess<<<(nwb * 32 + 255) / 256, 256, 0, c->stream>>>(wa);
   kd_walk<<<(nwb + 127) / 128, 128, 0, c->stream>>>(wa);
@@ -1121,7 +1310,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
       out->n_launches += 1;
     }
     CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
-    CU_TRY(c, cudaMemcpyAsync(&h_exit, d.d_exit + (nb - 1), 8, cudaMemcpyDeviceToHost, c->stream));
+    CU_TRY(c, cudaMemcpyAsync(&h_exit, d.d_exit + (walk_end - 1), 8, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     if (nwb <= 1 || !h_cnt[2]) break;
     if (round >= 256) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: record chain did not settle");
@@ -1131,8 +1320,10 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     kd_walk<<<(nwb + 127) / 128, 128, 0, c->stream>>>(wa);
     CU_TRY(c, cudaGetLastError());
   }
-  if (h_exit != total) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: record chain does not end at the end of the stream");
-  kd_scan_items<<<1, 1024, 0, c->stream>>>(d.d_nrec, d.d_ncig, first_block, nb, d.d_rec_base, d.d_cig_base, (uint64_t*)(d.d_cnt + 6));
+  if (walk_end == nb ? h_exit != stream_total : (h_exit == WALK_UNKNOWN || h_exit > total))
+    return fail(c, CMB_E_DECLINED, walk_end == nb ? "cmb_submit_bgzf: record chain does not end at the end of the stream"
+                                                  : "cmb_submit_bgzf: a record runs past the inflated tail of the block range");
+  kd_scan_items<<<1, 1024, 0, c->stream>>>(d.d_nrec, d.d_ncig, first_block, walk_end, d.d_rec_base, d.d_cig_base, (uint64_t*)(d.d_cnt + 6));
   CU_TRY(c, cudaGetLastError());
   out->n_launches += 1;
   uint64_t totals[2] = {0, 0};
@@ -1160,12 +1351,14 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     d.last_n_rec = (uint32_t)n_rec;
     d.last_n_cig = (uint32_t)n_cig;
     OffsetArgs oa{};
-    oa.data = d.d_inflated; oa.ustart = d.d_ustart; oa.guess = d.d_guess; oa.rec_base = d.d_rec_base; oa.cig_base = d.d_cig_base;
-    oa.first_block = first_block; oa.n_blocks = nb; oa.rec_off = d.d_rec_off; oa.iv_begin = tb.iv_begin; oa.n_records = n_rec; oa.n_cig_total = n_cig;
-    kd_offsets<<<(nwb + 127) / 128, 128, 0, c->stream>>>(oa);
+    oa.data = infl_base; oa.ustart = d.d_ustart; oa.guess = d.d_guess; oa.rec_base = d.d_rec_base; oa.cig_base = d.d_cig_base;
+    oa.first_block = first_block; oa.n_blocks = walk_end; oa.rec_off = d.d_rec_off; oa.iv_begin = tb.iv_begin; oa.n_records = n_rec; oa.n_cig_total = n_cig;
+    kd_offsets<<<(walk_end - first_block + 127) / 128, 128, 0, c->stream>>>(oa);
     CU_TRY(c, cudaGetLastError());
     ExtractArgs ea{};
-    ea.data = d.d_inflated; ea.rec_off = d.d_rec_off; ea.n_records = n_rec;
+    ea.data = infl_base; ea.rec_off = d.d_rec_off; ea.n_records = n_rec;
+    ea.own_lo = in->ranged ? in->own_tid_begin : INT_MIN; ea.own_hi = in->ranged ? in->own_tid_end : INT_MAX;
+    ea.own_unplaced = in->ranged ? in->own_unplaced : 1u; ea.n_owned = (unsigned long long*)(d.d_cnt + 10);
     ea.tid = tb.tid; ea.pos = tb.pos; ea.flag = tb.flag; ea.mapq = tb.mapq; ea.nm_state = tb.nm_state; ea.nm = tb.nm; ea.l_seq = tb.l_seq;
     ea.aligned = tb.aligned; ea.del = tb.del; ea.ins = tb.ins; ea.iv_begin = tb.iv_begin; ea.iv_start = tb.iv_start; ea.iv_len = tb.iv_len;
     ea.n_primary = (unsigned long long*)(d.d_cnt + 4); ea.flags = d.d_cnt + 1;
@@ -1176,10 +1369,22 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     if (h_cnt[1]) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: malformed alignment record (flags %u)", h_cnt[1]);
     memcpy(&out->n_primary, h_cnt + 4, 8);
+    memcpy(&out->n_records, h_cnt + 10, 8);  // records this call owns (all of them unless ranged)
     d.last_valid = true;
     CU_TRY(c, cudaEventRecord(d.ev[4], c->stream));
     if (c->n_local) {
-      rc = launch_k1(c, tb, (uint32_t)n_rec, (uint32_t)n_cig);
+      // records that start before excl_end_block are this rank's exclusive share of the stream (cmb_kept_tid_range)
+      uint32_t excl_n = 0xffffffffu;
+      if (in->ranged && in->excl_end_block < walk_end) {
+        if (in->excl_end_block <= first_block) excl_n = 0;
+        else {
+          uint64_t base = 0;
+          CU_TRY(c, cudaMemcpyAsync(&base, d.d_rec_base + in->excl_end_block, 8, cudaMemcpyDeviceToHost, c->stream));
+          CU_TRY(c, cudaStreamSynchronize(c->stream));
+          excl_n = (uint32_t)base;
+        }
+      }
+      rc = launch_k1(c, tb, (uint32_t)n_rec, (uint32_t)n_cig, excl_n);
       if (rc) return rc;
     }
   } else {

@@ -27,6 +27,10 @@ struct K1Args {
   cmb_contig_stats* rows;
   int2* block_minmax;  // per block {min kept tid, max kept tid} for the cross-block sortedness check
   uint32_t* error_flags;
+  // cross-RANK half of the sortedness check (multi-GPU): kept tid range of the records with index < excl_n, as
+  // kept_range[0] = max(tid + 1), kept_range[1] = max(INT_MAX - tid)  (0 = none yet)
+  uint32_t* kept_range;
+  uint32_t excl_n;
   // params
   cmb_params p;
   uint8_t filter_single, filter_pairs;
@@ -139,6 +143,15 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
     for (int d = 16; d > 0; d >>= 1) kmin = min(kmin, __shfl_xor_sync(FULL, kmin, d));
     if (lane == 31) s_wmax[warp] = pm;
     if (lane == 0) s_wmin[warp] = kmin;
+    {
+      const bool xk = keep && i < a.excl_n;
+      const uint32_t xmax = __reduce_max_sync(FULL, xk ? (uint32_t)tid + 1u : 0u);
+      const uint32_t xmin = __reduce_max_sync(FULL, xk ? (uint32_t)(INT_MAX - tid) : 0u);
+      if (lane == 0 && xmax) {
+        atomicMax(a.kept_range + 0, xmax);
+        atomicMax(a.kept_range + 1, xmin);
+      }
+    }
     __syncthreads();
     int before = INT_MIN;
     for (uint32_t w = 0; w < warp; ++w) before = max(before, s_wmax[w]);

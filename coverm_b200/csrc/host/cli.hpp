@@ -14,6 +14,7 @@
 #include <memory>
 #include <iostream>
 #include <sstream>
+#include <thread>
 
 #include "drivers.hpp"
 
@@ -34,6 +35,7 @@ struct CliOptions {
   bool single_genome = false, lib_streaming = false, print_reads_mapped = false, timing = false, quiet = false;
   int threads = 1;
   int device = 0;
+  int gpus = 1;  // > 1: every sample is range-partitioned by contig over GPUs device .. device+gpus-1 (one NCCL gather per sample)
 };
 
 struct CliResult {
@@ -106,6 +108,7 @@ inline CliOptions parse_cli(const std::vector<std::string>& args) {
     else if (a == "--genome-definition" && o.sub == "genome") o.genome_definition = value();
     else if (a == "-t" || a == "--threads") o.threads = std::stoi(value());
     else if (a == "--device") o.device = std::stoi(value());
+    else if (a == "--gpus") o.gpus = std::max(1, std::stoi(value()));
     else if (a == "--lib-estimators") o.lib_estimators = value();
     else if (a == "--lib-flags") o.lib_flags = value();
     else if (a == "--lib-streaming") o.lib_streaming = true;
@@ -294,8 +297,9 @@ inline Plan make_plan(const CliOptions& o) {
   return p;
 }
 
-// Runs one CLI invocation.  `memory_inputs` optionally supplies BAM bytes for paths given with -b (matched by path).
-inline CliResult run_cli(const std::vector<std::string>& args, const std::vector<InputSpec>& memory_inputs, std::ostream& out,
+// Runs one CLI invocation on one session (one rank).  `memory_inputs` optionally supplies BAM bytes for paths given with -b
+// (matched by path).
+inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::vector<InputSpec>& memory_inputs, std::ostream& out,
                          std::ostream& err, DeviceSession* shared_session = nullptr) {
   CliResult res;
   try {
@@ -382,6 +386,52 @@ inline CliResult run_cli(const std::vector<std::string>& args, const std::vector
     err << "thread 'main' panicked: " << e.what() << '\n';
     res.status = 101;
   }
+  return res;
+}
+
+// Runs one CLI invocation.  With `--gpus N` (and no session handed in) the process drives N GPUs itself: one session and one
+// host thread per GPU, an NCCL communicator over them (cmb_comm_init_local), every sample range-partitioned by contig
+// (DeviceSession::process in group mode); each rank then runs the ordinary driver on the gathered table and rank 0's
+// output is the result.
+inline CliResult run_cli(const std::vector<std::string>& args, const std::vector<InputSpec>& memory_inputs, std::ostream& out,
+                         std::ostream& err, DeviceSession* shared_session = nullptr) {
+  int gpus = 1, device = 0, threads = 1;
+  for (size_t i = 1; i + 1 < args.size(); ++i) {
+    try {
+      if (args[i] == "--gpus") gpus = std::max(1, std::stoi(args[i + 1]));
+      else if (args[i] == "--device") device = std::stoi(args[i + 1]);
+      else if (args[i] == "-t" || args[i] == "--threads") threads = std::stoi(args[i + 1]);
+    } catch (...) {  // malformed numbers are reported by parse_cli below
+    }
+  }
+  if (shared_session || gpus <= 1) return run_cli_rank(args, memory_inputs, out, err, shared_session);
+  std::vector<std::unique_ptr<DeviceSession>> sessions;
+  try {
+    std::vector<cmb_ctx*> ctxs;
+    for (int r = 0; r < gpus; ++r) {
+      sessions.push_back(std::make_unique<DeviceSession>(device + r, std::max(1, threads / gpus)));
+      ctxs.push_back(sessions.back()->ctx());
+    }
+    const int rc = cmb_comm_init_local(ctxs.data(), gpus);
+    if (rc) throw ExitError(1, std::string("cannot create the NCCL communicator over the GPUs: ") + cmb_last_error(ctxs[0]));
+    for (int r = 0; r < gpus; ++r) sessions[(size_t)r]->adopt_local_group(r, gpus);
+  } catch (const std::exception& e) {
+    err << "[ERROR] " << e.what() << '\n';
+    CliResult res;
+    res.status = 1;
+    return res;
+  }
+  std::vector<std::thread> others;
+  for (int r = 1; r < gpus; ++r)
+    others.emplace_back([&, r]() {
+      std::ostringstream o, e;  // the other ranks compute the same table; only rank 0's text is kept
+      std::vector<std::string> a = args;
+      for (size_t i = 1; i + 1 < a.size(); ++i)
+        if (a[i] == "-o" || a[i] == "--output-file") a[i + 1] = "-";
+      run_cli_rank(a, memory_inputs, o, e, sessions[(size_t)r].get());
+    });
+  CliResult res = run_cli_rank(args, memory_inputs, out, err, sessions[0].get());
+  for (auto& t : others) t.join();
   return res;
 }
 

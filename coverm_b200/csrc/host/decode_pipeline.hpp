@@ -88,6 +88,22 @@ class BlockIndex {
   }
 };
 
+// A BAM record header that could be real: sane block_size, reference ids, name length and NUL, field sizes.  Shared by
+// the speculative record alignment of the host decoder (decode_runner.hpp) and the block-range probe below.
+inline bool record_plausible(const uint8_t* buf, size_t s, size_t usize, uint32_t n_ref) {
+  if (s + 36 > usize) return false;
+  const uint32_t bs = rd_u32(buf + s);
+  if (bs < 32 || bs > (64u << 20)) return false;
+  const int32_t tid = (int32_t)rd_u32(buf + s + 4), pos = (int32_t)rd_u32(buf + s + 8), mtid = (int32_t)rd_u32(buf + s + 24);
+  if (tid < -1 || tid >= (int32_t)n_ref || mtid < -1 || mtid >= (int32_t)n_ref || pos < -1) return false;
+  const uint32_t l_name = buf[s + 12], n_cig = rd_u16(buf + s + 16), l_seq = rd_u32(buf + s + 20);
+  if (l_name == 0 || l_seq > (1u << 28)) return false;
+  const uint64_t fixed = 32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq;
+  if (fixed > bs) return false;
+  if (s + 36 + l_name <= usize && buf[s + 36 + l_name - 1] != 0) return false;
+  return true;
+}
+
 // Decode the fixed fields, CIGAR summary and NM aux of one BAM record; M/=/X blocks (contig.rs:171-186) are written to
 // ivs/ivl (room for n_cigar_op entries).  Returns the number of intervals written.
 inline uint32_t decode_bam_record_into(const uint8_t* rec, Tuple& t, int32_t* ivs, int32_t* ivl) {

@@ -253,20 +253,7 @@ PipelineCounts run_decode_pipeline(const BlockIndex& bx, uint64_t records_at, ui
     }
   };
 
-  // A plausible BAM record header at buf[s..): sane block_size, reference ids, name length and NUL, field sizes.
-  auto plausible = [&](const uint8_t* buf, size_t s, size_t usize) {
-    if (s + 36 > usize) return false;
-    const uint32_t bs = rd_u32(buf + s);
-    if (bs < 32 || bs > (64u << 20)) return false;
-    const int32_t tid = (int32_t)rd_u32(buf + s + 4), pos = (int32_t)rd_u32(buf + s + 8), mtid = (int32_t)rd_u32(buf + s + 24);
-    if (tid < -1 || tid >= (int32_t)n_ref || mtid < -1 || mtid >= (int32_t)n_ref || pos < -1) return false;
-    const uint32_t l_name = buf[s + 12], n_cig = rd_u16(buf + s + 16), l_seq = rd_u32(buf + s + 20);
-    if (l_name == 0 || l_seq > (1u << 28)) return false;
-    const uint64_t fixed = 32ull + l_name + 4ull * n_cig + (l_seq + 1) / 2 + l_seq;
-    if (fixed > bs) return false;
-    if (s + 36 + l_name <= usize && buf[s + 36 + l_name - 1] != 0) return false;
-    return true;
-  };
+  auto plausible = [&](const uint8_t* buf, size_t s, size_t usize) { return record_plausible(buf, s, usize, n_ref); };
   // Guess the first record boundary of an item and pre-walk its block_size chain while the data is cache-hot.
   auto prewalk = [&](Item& it, WorkCtx& w, size_t index) {
     const uint8_t* buf = w.buf.get();

@@ -96,6 +96,17 @@ int cmbh_session_set_shard(cmbh_session* s, uint32_t tid_begin, uint32_t tid_end
   return 0;
 }
 
+int cmbh_session_set_group(cmbh_session* s, int rank, int n_ranks, const uint8_t* nccl_id, cmbh_allgather_fn allgather, void* user) {
+  if (!s) return -2;
+  try {
+    s->dev->set_group(rank, n_ranks, nccl_id, allgather, user);
+    return 0;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 void* cmbh_session_ctx(cmbh_session* s) { return s ? (void*)s->dev->ctx() : nullptr; }
 
 int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_input* mem, int n_mem, cmbh_result* res) {
@@ -150,6 +161,13 @@ int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_
     si.decode_chain_ms = t.bgzf.ms_chain;
     si.decode_extract_ms = t.bgzf.ms_extract;
     si.decode_launches = t.decode_launches;
+    si.group_ranks = t.group_ranks;
+    si.shard_blocks = t.shard_blocks;
+    si.total_blocks = t.total_blocks;
+    si.range_probes = t.range_probes;
+    si.tid_begin = t.tid_begin;
+    si.tid_end = t.tid_end;
+    si.gather_s = t.gather_s;
   }
   return 0;
 }

@@ -7,6 +7,7 @@
 
 #include "bam_source.hpp"
 #include "decode_runner.hpp"
+#include "shard_range.hpp"
 
 namespace cmbh {
 
@@ -29,6 +30,9 @@ struct SampleTiming {
   bool device_decode = false;
   cmb_bgzf_result bgzf{};
   uint32_t decode_launches = 0;
+  // multi-GPU contig sharding
+  uint32_t group_ranks = 1, shard_blocks = 0, total_blocks = 0, range_probes = 0, tid_begin = 0, tid_end = 0;
+  double gather_s = 0;
 };
 
 struct SampleResult {
@@ -197,7 +201,191 @@ class DeviceSession {
   // Restrict this session to the contig shard [begin, end) (multi-GPU); (0, UINT32_MAX) = everything.
   void set_shard(uint32_t begin, uint32_t end) { shard_begin_ = begin; shard_end_ = end; ref_lens_.clear(); }
 
+  // Makes this session rank `rank` of `n_ranks` that process every sample TOGETHER (contigs range-partitioned by summed
+  // length, each rank decoding only its BGZF block range, one gather of the per-contig table).  The ranks
+  // exchange either over NCCL inside the device library (`nccl_id` from cmb_comm_unique_id, shared by the caller) or, for
+  // hosts without NCCL between them (MPI, gloo, tests), through the caller's own all-gather of host buffers.
+  typedef int (*AllGatherFn)(void* user, const void* send, size_t bytes_per_rank, void* recv);
+  void set_group(int rank, int n_ranks, const uint8_t* nccl_id, AllGatherFn fn, void* user) {
+    if (n_ranks < 1 || rank < 0 || rank >= n_ranks) throw ExitError(1, "set_group: bad rank / group size");
+    if (n_ranks > 1 && !nccl_id && !fn) throw ExitError(1, "set_group: a group needs an NCCL id or an all-gather callback");
+    if (group_nccl_) cmb_comm_destroy(ctx_);
+    group_rank_ = rank;
+    group_n_ = n_ranks;
+    group_nccl_ = false;
+    group_fn_ = fn;
+    group_user_ = user;
+    if (n_ranks > 1 && nccl_id) {
+      const int rc = cmb_comm_init(ctx_, nccl_id, rank, n_ranks);
+      if (rc) throw ExitError(1, std::string("cannot create the NCCL communicator: ") + cmb_last_error(ctx_));
+      group_nccl_ = true;
+    }
+    ref_lens_.clear();
+  }
+  // cmb_comm_init_local was called on this session's context by the owner of all the ranks (one process, several GPUs)
+  void adopt_local_group(int rank, int n_ranks) {
+    group_rank_ = rank;
+    group_n_ = n_ranks;
+    group_nccl_ = n_ranks > 1;
+    group_fn_ = nullptr;
+    ref_lens_.clear();
+  }
+  int group_rank() const { return group_rank_; }
+  int group_size() const { return group_n_; }
+
+  // One sample.  In a group every rank must call this for the same input (it is collective).
   SampleResult process(const InputSpec& in, const cmb_params& params) {
+    if (group_n_ <= 1) return process_local(in, params, nullptr);
+    // ---- local phase: this rank's contigs, from this rank's block range.  Nothing may escape before the ranks have
+    //      compared notes: a rank that failed still takes part in the exchange, and then every rank fails the same way.
+    ShardState sh;
+    SampleResult res;
+    RankSummary mine{};
+    try {
+      res = process_local(in, params, &sh);
+      mine.n_records = res.n_records;
+      mine.n_primary = res.num_detected_primary_alignments;
+      mine.counts_global = sh.counts_global ? 1 : 0;
+      mine.n_pairs = sh.n_pairs;
+      int32_t lo = INT32_MAX, hi = INT32_MIN;
+      if (!sh.counts_global) cmb_kept_tid_range(ctx_, &lo, &hi);
+      mine.min_tid = lo;
+      mine.max_tid = hi;
+    } catch (const Panic& e) {
+      mine.kind = 1;
+      mine.code = 101;
+      snprintf(mine.message, sizeof mine.message, "%s", e.what());
+    } catch (const ExitError& e) {
+      mine.kind = 2;
+      mine.code = e.code;
+      snprintf(mine.message, sizeof mine.message, "%s", e.what());
+    } catch (const std::exception& e) {
+      mine.kind = 1;
+      mine.code = 101;
+      snprintf(mine.message, sizeof mine.message, "%s", e.what());
+    }
+    const double t_g0 = now_s();
+    std::vector<RankSummary> all((size_t)group_n_);
+    group_allgather(&mine, all.data(), sizeof(RankSummary));
+    for (const RankSummary& s : all) {  // the lowest failing rank's error, on every rank
+      if (s.kind == 1) throw Panic(s.message);
+      if (s.kind == 2) throw ExitError(s.code, s.message);
+    }
+    // cross-rank half of the sortedness check (contig.rs:129-132): each rank has verified its own (overlapping) stretch of
+    // the stream; the kept tids of the ranks' exclusive shares must not decrease from rank to rank either
+    {
+      int64_t seen_max = INT64_MIN;
+      for (const RankSummary& s : all) {
+        if (s.counts_global || s.min_tid > s.max_tid) continue;
+        if ((int64_t)s.min_tid < seen_max)
+          throw Panic("BAM file appears to be unsorted. Input BAM files must be sorted by reference (i.e. by samtools sort)");
+        seen_max = std::max<int64_t>(seen_max, s.max_tid);
+      }
+    }
+    // ---- the gather of the path: every rank ends up with the complete per-contig table (+ histogram pairs)
+    const uint32_t n_ref = (uint32_t)res.hdr->names.size();
+    std::vector<uint64_t> pair_base((size_t)group_n_ + 1, 0);
+    for (int r = 0; r < group_n_; ++r) pair_base[(size_t)r + 1] = pair_base[(size_t)r] + all[(size_t)r].n_pairs;
+    const bool csr = params.want & CMB_WANT_HIST_CSR;
+    res.pairs.clear();
+    if (csr) res.pairs.resize(pair_base[(size_t)group_n_]);
+    ensure_rows(n_ref);
+    if (group_nccl_) {
+      const int rc = cmb_allgather_stats(ctx_, sh.cuts.data(), csr ? pair_base.data() : nullptr, rows_buf_, csr ? res.pairs.data() : nullptr);
+      if (rc) throw_device_error(ctx_, rc);
+    } else {
+      gather_rows_through_host(sh, res, all, pair_base, csr);
+    }
+    res.rows = rows_buf_;
+    // whole-file counters: summed over the ranks' owned records -- or taken from a rank that had to read the whole file
+    uint64_t n_rec = 0, n_pri = 0;
+    bool have_global = false;
+    for (const RankSummary& s : all) {
+      if (s.counts_global) {
+        if (!have_global) {
+          n_rec = s.n_records;
+          n_pri = s.n_primary;
+          have_global = true;
+        }
+      } else if (!have_global) {
+        n_rec += s.n_records;
+        n_pri += s.n_primary;
+      }
+    }
+    res.n_records = n_rec;
+    res.num_detected_primary_alignments = n_pri;
+    res.timing.gather_s = now_s() - t_g0;
+    res.timing.total_s += res.timing.gather_s;
+    res.timing.group_ranks = (uint32_t)group_n_;
+    return res;
+  }
+
+ private:
+  struct ShardState {
+    std::vector<uint32_t> cuts;
+    bool counts_global = false;  // this rank read the whole file (host decode): its counters cover every record
+    uint64_t n_pairs = 0;
+  };
+  struct RankSummary {  // what the ranks tell each other before the table gather (fixed size: it travels by all-gather)
+    int32_t kind;       // 0 fine, 1 Panic, 2 ExitError
+    int32_t code;
+    uint64_t n_records, n_primary, n_pairs;
+    int32_t min_tid, max_tid;
+    uint32_t counts_global, reserved;
+    char message[208];
+  };
+
+  void group_allgather(const void* send, void* recv, size_t bytes) {
+    if (group_nccl_) {
+      const int rc = cmb_comm_allgather(ctx_, send, recv, bytes);
+      if (rc) throw ExitError(1, std::string("all-gather over NCCL failed: ") + cmb_last_error(ctx_));
+    } else if (group_fn_(group_user_, send, bytes, recv) != 0) {
+      throw ExitError(1, "the caller's all-gather failed");
+    }
+  }
+
+  void ensure_rows(uint32_t n_ref) {
+    if (rows_cap_ < (size_t)n_ref + 1) {
+      cmb_host_free(rows_buf_);
+      rows_cap_ = 0;
+      rows_buf_ = (cmb_contig_stats*)cmb_host_alloc(sizeof(cmb_contig_stats) * ((size_t)n_ref + 1));
+      if (!rows_buf_) throw ExitError(1, "cannot allocate the page-locked result buffer");
+      rows_cap_ = (size_t)n_ref + 1;
+    }
+  }
+
+  // Table gather without NCCL: own row range (and own pairs, offsets made global) through the caller's all-gather, padded
+  // to the largest share.
+  void gather_rows_through_host(const ShardState& sh, SampleResult& res, const std::vector<RankSummary>& all,
+                                const std::vector<uint64_t>& pair_base, bool csr) {
+    const int N = group_n_, me = group_rank_;
+    size_t max_rows = 0, max_pairs = 0;
+    for (int r = 0; r < N; ++r) {
+      max_rows = std::max<size_t>(max_rows, sh.cuts[(size_t)r + 1] - sh.cuts[(size_t)r]);
+      max_pairs = std::max<size_t>(max_pairs, all[(size_t)r].n_pairs);
+    }
+    const uint32_t b = sh.cuts[(size_t)me], e = sh.cuts[(size_t)me + 1];
+    if (max_rows) {
+      std::vector<cmb_contig_stats> send(max_rows), recv(max_rows * (size_t)N);
+      for (uint32_t t = b; t < e; ++t) {
+        send[t - b] = rows_buf_[t];
+        if (csr && send[t - b].hist_count) send[t - b].hist_offset += pair_base[(size_t)me];
+      }
+      group_allgather(send.data(), recv.data(), max_rows * sizeof(cmb_contig_stats));
+      for (int r = 0; r < N; ++r)
+        for (uint32_t t = sh.cuts[(size_t)r]; t < sh.cuts[(size_t)r + 1]; ++t) rows_buf_[t] = recv[(size_t)r * max_rows + (t - sh.cuts[(size_t)r])];
+    }
+    if (csr && max_pairs) {
+      std::vector<cmb_hist_pair> send(max_pairs), recv(max_pairs * (size_t)N);
+      std::copy(local_pairs_.begin(), local_pairs_.end(), send.begin());
+      group_allgather(send.data(), recv.data(), max_pairs * sizeof(cmb_hist_pair));
+      for (int r = 0; r < N; ++r)
+        std::copy(recv.begin() + (ptrdiff_t)((size_t)r * max_pairs), recv.begin() + (ptrdiff_t)((size_t)r * max_pairs + all[(size_t)r].n_pairs),
+                  res.pairs.begin() + (ptrdiff_t)pair_base[(size_t)r]);
+    }
+  }
+
+  SampleResult process_local(const InputSpec& in, const cmb_params& params, ShardState* shard) {
     SampleResult res;
     const double t0 = now_s();
     res.stoit_name = file_stem(in.path);
@@ -262,8 +450,17 @@ class DeviceSession {
     begin += records_at;
 
     // ---- device reference + params
-    const uint32_t sb = std::min<uint32_t>(shard_begin_, n_ref), se = std::min<uint32_t>(shard_end_, n_ref);
-    if (res.hdr->lens != ref_lens_) {
+    uint32_t sb = std::min<uint32_t>(shard_begin_, n_ref), se = std::min<uint32_t>(shard_end_, n_ref);
+    if (shard) {
+      shard->cuts = tid_cuts_by_length(res.hdr->lens, group_n_);
+      sb = shard->cuts[(size_t)group_rank_];
+      se = shard->cuts[(size_t)group_rank_ + 1];
+    }
+    res.timing.tid_begin = sb;
+    res.timing.tid_end = se;
+    if (res.hdr->lens != ref_lens_ || sb != ref_sb_ || se != ref_se_) {
+      ref_sb_ = sb;
+      ref_se_ = se;
       rc = cmb_set_reference(ctx_, n_ref, res.hdr->lens.data(), sb, se);
       if (rc) throw_device_error(ctx_, rc);
       ref_lens_ = res.hdr->lens;
@@ -348,9 +545,30 @@ class DeviceSession {
         bi.block_isize = isz.data();
         bi.records_at = records_at;
         bi.copy_threads = (uint32_t)std::min(pool_.size(), 8);
+        bool range_ok = true;
+        if (shard) {  // this rank's block range (shard_range.hpp); a stream whose alignment cannot be confirmed is read whole
+          try {
+            BlockRangeFinder finder(bx, n_ref, records_at);
+            const bool last = group_rank_ == group_n_ - 1;
+            const BlockRange br = finder.find(sb, se, group_rank_ == 0, last);
+            bi.ranged = 1;
+            bi.walk_begin_block = br.walk_begin;
+            bi.walk_end_block = br.walk_end;
+            bi.records_at = br.records_at;
+            bi.excl_end_block = br.excl_end;
+            bi.own_tid_begin = (int32_t)sb;
+            bi.own_tid_end = (int32_t)se;
+            bi.own_unplaced = last ? 1u : 0u;
+            res.timing.shard_blocks = br.walk_end - br.walk_begin;
+            res.timing.total_blocks = (uint32_t)nb;
+            res.timing.range_probes = br.probes;
+          } catch (const Panic&) {
+            range_ok = false;
+          }
+        }
         cmb_bgzf_result br{};
         const double a = now_s();
-        const int r2 = cmb_submit_bgzf(ctx_, &bi, &br);
+        const int r2 = range_ok ? cmb_submit_bgzf(ctx_, &bi, &br) : CMB_E_DECLINED;
         if (r2 == CMB_OK) {
           decoded_on_device = true;
           res.timing.device_decode = true;
@@ -369,6 +587,7 @@ class DeviceSession {
         }
       }
       if (!decoded_on_device) {
+      if (shard) shard->counts_global = true;  // every rank's host decoder reads the whole file; K1 keeps the rank's own tids
       const PipelineCounts pc = run_decode_pipeline(
           bx, records_at, n_ref, pool_.size(), batch_records_, batch_intervals_, n_staging_, scratch_,
           [&](cmb_read_batch* b) {
@@ -390,6 +609,7 @@ class DeviceSession {
                 pc.n_items, pc.n_workers, pc.inflate_s, pc.scan_s, pc.extract_s, pc.idle_s);
       }
     } else for (;;) {
+      if (shard) shard->counts_global = true;  // mate matching reads the whole file on every rank
       // complete records currently in buf
       rec_off.clear();
       size_t q = begin;
@@ -466,21 +686,26 @@ class DeviceSession {
     }
     const double t_dec = now_s();
     submit();
-    if (rows_cap_ < (size_t)n_ref + 1) {
-      cmb_host_free(rows_buf_);
-      rows_cap_ = 0;
-      rows_buf_ = (cmb_contig_stats*)cmb_host_alloc(sizeof(cmb_contig_stats) * ((size_t)n_ref + 1));
-      if (!rows_buf_) throw ExitError(1, "cannot allocate the page-locked result buffer");
-      rows_cap_ = (size_t)n_ref + 1;
-    }
+    ensure_rows(n_ref);
     res.rows = rows_buf_;
     uint64_t n_pairs = 0;
-    rc = cmb_end_sample(ctx_, rows_buf_, nullptr, 0, &n_pairs);
-    if (rc) throw_device_error(ctx_, rc);
-    if ((params.want & CMB_WANT_HIST_CSR) && n_pairs) {
-      res.pairs.resize(n_pairs);
-      rc = cmb_fetch_pairs(ctx_, res.pairs.data(), n_pairs);
+    if (shard && group_nccl_) {
+      // rows (and pairs) stay on the device: cmb_allgather_stats completes the table there and copies it back once
+      rc = cmb_end_sample(ctx_, nullptr, nullptr, 0, &n_pairs);
       if (rc) throw_device_error(ctx_, rc);
+      shard->n_pairs = n_pairs;
+    } else {
+      rc = cmb_end_sample(ctx_, rows_buf_, nullptr, 0, &n_pairs);
+      if (rc) throw_device_error(ctx_, rc);
+      if ((params.want & CMB_WANT_HIST_CSR) && n_pairs) {
+        res.pairs.resize(n_pairs);
+        rc = cmb_fetch_pairs(ctx_, res.pairs.data(), n_pairs);
+        if (rc) throw_device_error(ctx_, rc);
+      }
+      if (shard) {
+        shard->n_pairs = n_pairs;
+        local_pairs_ = res.pairs;
+      }
     }
     cmb_get_timing(ctx_, &res.timing.device);
     if (!res.timing.device_decode) res.timing.h2d_bytes = 40ull * res.timing.device.n_records + 4 + 8ull * res.timing.device.n_intervals;
@@ -492,7 +717,6 @@ class DeviceSession {
     return res;
   }
 
- private:
   std::shared_ptr<Header> hdr_cache_;  // parsed reference list of the previous sample and its raw bytes (n_ref .. first record)
   std::vector<uint8_t> hdr_raw_;
   cmb_contig_stats* rows_buf_ = nullptr;
@@ -503,6 +727,13 @@ class DeviceSession {
   uint32_t batch_records_ = 0, batch_intervals_ = 0, n_staging_ = 0;
   uint32_t shard_begin_ = 0, shard_end_ = 0xffffffffu;
   std::vector<uint64_t> ref_lens_;
+  uint32_t ref_sb_ = 0, ref_se_ = 0;
+  // group (multi-GPU contig sharding)
+  int group_rank_ = 0, group_n_ = 1;
+  bool group_nccl_ = false;
+  AllGatherFn group_fn_ = nullptr;
+  void* group_user_ = nullptr;
+  std::vector<cmb_hist_pair> local_pairs_;
 };
 
 }  // namespace cmbh

@@ -40,7 +40,7 @@
 extern "C" {
 #endif
 
-#define CMB_ABI_VERSION 2
+#define CMB_ABI_VERSION 3
 
 /* error codes */
 #define CMB_OK 0
@@ -189,7 +189,8 @@ int cmb_submit_batch(cmb_ctx* ctx, uint32_t n_records, uint32_t n_intervals);   
 /* Device-resident input variant (all pointers are DEVICE pointers laid out as cmb_read_batch;
  * used for device-only timing and by hosts that already stage tuples in HBM). */
 int cmb_submit_device_batch(cmb_ctx* ctx, const cmb_read_batch* dev_batch, uint32_t n_records, uint32_t n_intervals);
-/* Scan + reduce + copy back.  `stats` has n_contigs rows (rows outside the shard are zeroed).
+/* Scan + reduce + copy back.  `stats` has n_contigs rows (rows outside the shard are zeroed); NULL leaves the rows on the
+ * device (a multi-GPU caller completes the table there with cmb_allgather_stats and copies it back once).
  * `pairs`/`pairs_capacity` receive the CSR histogram when CMB_WANT_HIST_CSR is set (may be NULL otherwise);
  * *n_pairs gets the number of pairs produced. */
 int cmb_end_sample(cmb_ctx* ctx, cmb_contig_stats* stats, cmb_hist_pair* pairs, uint64_t pairs_capacity,
@@ -218,9 +219,19 @@ typedef struct cmb_bgzf_input {
   const uint64_t* block_coffset;  /* per BGZF block: offset of its deflate payload in `data`           */
   const uint32_t* block_clen;     /* payload length (the 8-byte CRC32/ISIZE footer follows it)         */
   const uint32_t* block_isize;    /* uncompressed size                                                 */
-  uint64_t records_at;            /* uncompressed offset of the first alignment record                 */
+  uint64_t records_at;            /* uncompressed offset of the first alignment record to decode       */
   uint32_t copy_threads;          /* 0 = 4                                                             */
-  uint32_t reserved;
+  uint32_t ranged;                /* 0: the whole file.  1: only a block range of it (multi-GPU contig sharding: a
+                                     reference-sorted BAM keeps a tid range in a contiguous run of blocks, so each
+                                     rank uploads and inflates only its share) -- the fields below apply          */
+  uint32_t walk_begin_block;      /* block holding `records_at`                                         */
+  uint32_t walk_end_block;        /* records STARTING in blocks [walk_begin_block, walk_end_block) are decoded; the
+                                     bytes of a record running past that come from the blocks that follow */
+  int32_t own_tid_begin;          /* result counters (n_records, n_primary) and the rank's sortedness summary count  */
+  int32_t own_tid_end;            /* only records with own_tid_begin <= tid < own_tid_end ...                        */
+  uint32_t own_unplaced;          /* ... plus, when set, records without a reference (tid < 0: the unmapped tail)   */
+  uint32_t excl_end_block;        /* neighbouring ranks' walks overlap by a block: records starting before this block are
+                                     this rank's EXCLUSIVE share of the stream (cmb_kept_tid_range)                  */
 } cmb_bgzf_input;
 typedef struct cmb_bgzf_result {
   uint64_t n_records;             /* alignment records in the file                                     */
@@ -241,6 +252,34 @@ int cmb_last_bgzf_batch(cmb_ctx* ctx, cmb_read_batch* dev_batch, uint32_t* n_rec
 
 /* Page-locked host memory for result buffers (cmb_end_sample copies straight into it at PCIe speed).  Plain malloc
  * semantics otherwise; free with cmb_host_free. */
+/* ---- Multi-GPU: one sample range-partitioned by contig over several GPUs -------------------------
+ * Contigs are independent (contig.rs flushes per tid), so each rank owns a tid range [tid_cuts[r], tid_cuts[r+1])
+ * (cmb_set_reference's shard), decodes only the BGZF blocks that hold it, and the per-contig tables are merged by ONE
+ * gather over NCCL (NVLink): every rank broadcasts its own row range in place, after which every rank's table is
+ * complete -- the global scalars of the printers (contig.rs:70-72, coverage_printer.rs:457-465) are then computed in
+ * entry order exactly as on one GPU.  One process per GPU: rank 0 calls cmb_comm_unique_id and shares the id out of
+ * band (torch.distributed, MPI, a file); one process driving several GPUs: cmb_comm_init_local. */
+#define CMB_COMM_ID_BYTES 128
+int cmb_comm_unique_id(uint8_t id[CMB_COMM_ID_BYTES]);
+int cmb_comm_init(cmb_ctx* ctx, const uint8_t id[CMB_COMM_ID_BYTES], int rank, int n_ranks);
+int cmb_comm_init_local(cmb_ctx* const* ctxs, int n_ranks); /* ctxs[r] becomes rank r */
+void cmb_comm_destroy(cmb_ctx* ctx);
+/* Small host-to-host all-gather over the communicator (`bytes` per rank, staged through device memory): rank summaries,
+ * error status, counters.  Collective: every rank must call it. */
+int cmb_comm_allgather(cmb_ctx* ctx, const void* send, void* recv, size_t bytes);
+/* The gather of the path.  Call after cmb_end_sample_device on every rank.  tid_cuts has n_ranks + 1 entries.  With
+ * CMB_WANT_HIST_CSR, pair_base (n_ranks + 1 entries: exclusive prefix sums of the ranks' pair counts, which the caller
+ * exchanged with cmb_comm_allgather) makes the histogram pairs global too: each rank's rows get hist_offset += its
+ * base before they travel, and the pair arrays are concatenated in rank order.  On return `stats` (n_contigs rows) and
+ * `pairs` (pair_base[n_ranks] entries; may be NULL) hold the complete table on every rank; the device copy of the
+ * table is complete as well (cmb_end_sample_device's pointer). */
+int cmb_allgather_stats(cmb_ctx* ctx, const uint32_t* tid_cuts, const uint64_t* pair_base, cmb_contig_stats* stats,
+                        cmb_hist_pair* pairs);
+/* Kept-record tid range of the rank's own part of the stream, for the cross-rank half of the sortedness check
+ * (contig.rs:129-132): smallest / largest tid among the records that passed the filters and START in this rank's
+ * exclusive share of the blocks; *min_tid > *max_tid when there is none.  Valid after cmb_end_sample*. */
+int cmb_kept_tid_range(cmb_ctx* ctx, int32_t* min_tid, int32_t* max_tid);
+
 void* cmb_host_alloc(size_t bytes);
 void cmb_host_free(void* p);
 

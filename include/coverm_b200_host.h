@@ -41,6 +41,12 @@ typedef struct cmbh_sample_info {
   uint32_t decode_host_blocks; /* BGZF blocks the device declined (inflated with zlib by the library) */
   float decode_copy_inflate_ms, decode_chain_ms, decode_extract_ms; /* device decode stages (CUDA events) */
   uint32_t decode_launches;  /* kernels launched by the device decode */
+  uint32_t group_ranks;      /* ranks that processed this sample together (1 = single GPU) */
+  uint32_t shard_blocks, total_blocks; /* BGZF blocks this rank walked / blocks in the file */
+  uint32_t range_probes;     /* blocks inflated on the host to find the rank's block range */
+  uint32_t tid_begin, tid_end; /* contigs this rank owned for the sample */
+  uint32_t reserved;
+  double gather_s;           /* summary exchange + table gather (wall clock) */
 } cmbh_sample_info;
 
 typedef struct cmbh_result {
@@ -61,6 +67,20 @@ void cmbh_session_destroy(cmbh_session* s);
 const char* cmbh_last_error(void);
 /* Restrict the session to contigs [tid_begin, tid_end) (multi-GPU contig sharding); rows outside come back zero. */
 int cmbh_session_set_shard(cmbh_session* s, uint32_t tid_begin, uint32_t tid_end);
+
+/* Multi-GPU, one sample at a time over all GPUs (the reference is single-process, src/contig.rs:22):
+ * make this session rank `rank` of `n_ranks`.  Every following cmbh_run is then COLLECTIVE -- each rank calls it with the
+ * same argv -- and per sample each rank owns a contig range (balanced by length), uploads and inflates only the BGZF
+ * blocks holding it, and one gather completes the per-contig table on every rank, after which the drivers and printers run
+ * as on one GPU (global scalars in entry order, src/contig.rs:70-72, src/coverage_printer.rs:457-465): every rank
+ * returns the same text; a caller normally keeps rank 0's.
+ *   nccl_id != NULL : the gather runs over NCCL inside the library (id from cmb_comm_unique_id on rank 0, shared by the
+ *                     caller -- torch.distributed broadcast, MPI, a file);
+ *   nccl_id == NULL : `allgather(user, send, bytes_per_rank, recv)` is the caller's own all-gather of host buffers
+ *                     (MPI / gloo between hosts without NCCL; the CPU tests).  Returns 0 on success.
+ * n_ranks == 1 leaves the group. */
+typedef int (*cmbh_allgather_fn)(void* user, const void* send, size_t bytes_per_rank, void* recv);
+int cmbh_session_set_group(cmbh_session* s, int rank, int n_ranks, const uint8_t* nccl_id, cmbh_allgather_fn allgather, void* user);
 
 /* The session's device context (a cmb_ctx* of coverm_b200.h), for callers that continue on the device ABI after a
  * cmbh_run -- e.g. re-running the kernels over the tuples the run left in HBM (cmb_last_bgzf_batch). */

@@ -35,6 +35,7 @@ struct cmb_ctx {
   std::vector<cmb_contig_stats> rows;
   std::vector<cmb_hist_pair> pairs;
   int64_t last_kept_tid = INT64_MIN;
+  int64_t excl_min = INT64_MAX, excl_max = INT64_MIN;  // kept tid range of the exclusive records (cmb_kept_tid_range)
   int error = 0;
   uint64_t n_records = 0, n_intervals = 0;
 };
@@ -100,6 +101,8 @@ int cmb_begin_sample(cmb_ctx* c) {
   c->rows.assign(c->lens.size(), cmb_contig_stats{});
   c->pairs.clear();
   c->last_kept_tid = INT64_MIN;
+  c->excl_min = INT64_MAX;
+  c->excl_max = INT64_MIN;
   c->error = 0;
   c->in_sample = true;
   c->ended = false;
@@ -130,7 +133,7 @@ static bool pair_ok(const Rec& a, const Rec& b, const cmb_params& p, bool* nm_er
          1.0f - ((float)((uint64_t)a.nm + b.nm) / (float)al) >= p.min_percent_identity_pair;
 }
 
-static int submit(cmb_ctx* c, const cmb_read_batch& b, uint32_t n, uint32_t ni) {
+static int submit(cmb_ctx* c, const cmb_read_batch& b, uint32_t n, uint32_t ni, uint32_t excl_n = 0xffffffffu) {
   const cmb_params& p = c->p;
   auto rec = [&](uint32_t i) { return Rec{b.flag[i], b.mapq[i], b.nm_state[i], b.nm[i], b.l_seq[i], b.aligned[i], b.del[i]}; };
   for (uint32_t i = 0; i < n; ++i) {
@@ -163,6 +166,10 @@ static int submit(cmb_ctx* c, const cmb_read_batch& b, uint32_t n, uint32_t ni) 
     if (tid < 0 || (size_t)tid >= c->lens.size()) { c->error |= 4; continue; }
     if (tid < c->last_kept_tid) c->error |= 1;
     c->last_kept_tid = std::max<int64_t>(c->last_kept_tid, tid);
+    if (i < excl_n) {
+      c->excl_min = std::min<int64_t>(c->excl_min, tid);
+      c->excl_max = std::max<int64_t>(c->excl_max, tid);
+    }
     if ((uint32_t)tid < c->tid_begin || (uint32_t)tid >= c->tid_end) continue;
     cmb_contig_stats& row = c->rows[tid];
     const bool primary = !sec && !sup;
@@ -215,8 +222,22 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
   }
   if (c->mode.filter_pairs) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: pair filtering needs host mate matching");
   *out = cmb_bgzf_result{};
+  // like the device: only the blocks of the range (plus a tail for its last straddling record) are inflated; `stream`
+  // is indexed with absolute uncompressed offsets through `base`
+  std::vector<uint64_t> ustart((size_t)in->n_blocks + 1, 0);
+  for (uint32_t b = 0; b < in->n_blocks; ++b) ustart[b + 1] = ustart[b] + in->block_isize[b];
+  uint32_t b_lo = 0, walk_end = in->n_blocks, data_end = in->n_blocks;
+  if (in->ranged) {
+    b_lo = in->walk_begin_block;
+    walk_end = in->walk_end_block;
+    if (walk_end <= b_lo) return CMB_OK;
+    data_end = walk_end;
+    uint64_t tail = 0;
+    while (data_end < in->n_blocks && tail < (4u << 20)) tail += in->block_isize[data_end++];
+  }
+  const uint64_t base = ustart[b_lo];
   std::vector<uint8_t> stream;
-  for (uint32_t b = 0; b < in->n_blocks; ++b) {
+  for (uint32_t b = b_lo; b < data_end; ++b) {
     const uint32_t isz = in->block_isize[b];
     const size_t at = stream.size();
     stream.resize(at + isz);
@@ -241,8 +262,12 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
   std::vector<uint16_t> flag;
   std::vector<uint8_t> mapq, nm_state;
   std::vector<uint32_t> nm, l_seq, aligned, del, ins, iv_begin;
-  size_t o = in->records_at;
-  while (o < stream.size()) {
+  size_t o = in->records_at - base;
+  const size_t walk_stop = (size_t)(ustart[walk_end] - base);  // records starting at or after this belong to the next range
+  size_t excl_n = (size_t)-1;
+  uint64_t n_owned = 0;
+  while (o < stream.size() && o < walk_stop) {
+    if (in->ranged && excl_n == (size_t)-1 && in->excl_end_block < walk_end && o >= (size_t)(ustart[in->excl_end_block] - base)) excl_n = tid.size();
     if (o + 36 > stream.size()) return fail(c, CMB_E_DECLINED, "emulator: record cut short");
     const uint32_t bs = u32(o);
     if (bs < 32 || o + 4 + (size_t)bs > stream.size()) return fail(c, CMB_E_DECLINED, "emulator: record cut short");
@@ -253,7 +278,9 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
     mapq.push_back(stream[r + 9]);
     flag.push_back((uint16_t)u16(r + 14));
     l_seq.push_back(ls);
-    if (!(flag.back() & 0x900)) out->n_primary += 1;
+    const bool owned = !in->ranged || (tid.back() < 0 ? in->own_unplaced != 0 : (tid.back() >= in->own_tid_begin && tid.back() < in->own_tid_end));
+    n_owned += owned;
+    if (owned && !(flag.back() & 0x900)) out->n_primary += 1;
     size_t cg = r + 32 + l_name;
     size_t aux = cg + 4ull * n_cig + (ls + 1) / 2 + ls;
     if (aux > end) return fail(c, CMB_E_DECLINED, "emulator: malformed record");
@@ -304,7 +331,7 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
     o = end;
   }
   iv_begin.push_back((uint32_t)ivs.size());
-  out->n_records = tid.size();
+  out->n_records = n_owned;
   out->n_intervals = ivs.size();
   out->h2d_bytes = in->size;
   if (tid.empty()) return CMB_OK;
@@ -313,7 +340,20 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
   b.tid = tid.data(); b.pos = pos.data(); b.flag = flag.data(); b.mapq = mapq.data(); b.nm_state = nm_state.data(); b.nm = nm.data();
   b.l_seq = l_seq.data(); b.aligned = aligned.data(); b.del = del.data(); b.ins = ins.data(); b.iv_begin = iv_begin.data();
   b.iv_start = ivs.data(); b.iv_len = ivl.data();
-  return submit(c, b, (uint32_t)tid.size(), (uint32_t)out->n_intervals);
+  return submit(c, b, (uint32_t)tid.size(), (uint32_t)out->n_intervals, excl_n == (size_t)-1 ? 0xffffffffu : (uint32_t)excl_n);
+}
+
+// No NCCL in the emulator: groups of emulated ranks exchange through the host all-gather callback of the session.
+int cmb_comm_unique_id(uint8_t*) { return fail(nullptr, CMB_E_ARG, "emulator: no NCCL"); }
+int cmb_comm_init(cmb_ctx* c, const uint8_t*, int, int) { return fail(c, CMB_E_ARG, "emulator: no NCCL"); }
+int cmb_comm_init_local(cmb_ctx* const*, int) { return fail(nullptr, CMB_E_ARG, "emulator: no NCCL"); }
+void cmb_comm_destroy(cmb_ctx*) {}
+int cmb_comm_allgather(cmb_ctx* c, const void*, void*, size_t) { return fail(c, CMB_E_ARG, "emulator: no NCCL"); }
+int cmb_allgather_stats(cmb_ctx* c, const uint32_t*, const uint64_t*, cmb_contig_stats*, cmb_hist_pair*) { return fail(c, CMB_E_ARG, "emulator: no NCCL"); }
+int cmb_kept_tid_range(cmb_ctx* c, int32_t* lo, int32_t* hi) {
+  *lo = c->excl_min == INT64_MAX ? INT32_MAX : (int32_t)c->excl_min;
+  *hi = c->excl_max == INT64_MIN ? INT32_MIN : (int32_t)c->excl_max;
+  return CMB_OK;
 }
 
 int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** out) {
@@ -373,7 +413,7 @@ int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** out) {
 int cmb_end_sample(cmb_ctx* c, cmb_contig_stats* stats, cmb_hist_pair* pairs, uint64_t cap, uint64_t* n_pairs) {
   int rc = cmb_end_sample_device(c, nullptr);
   if (rc) return rc;
-  memcpy(stats, c->rows.data(), sizeof(cmb_contig_stats) * c->rows.size());
+  if (stats) memcpy(stats, c->rows.data(), sizeof(cmb_contig_stats) * c->rows.size());
   if (pairs && cap >= c->pairs.size()) memcpy(pairs, c->pairs.data(), sizeof(cmb_hist_pair) * c->pairs.size());
   if (n_pairs) *n_pairs = c->pairs.size();
   return CMB_OK;

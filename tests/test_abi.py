@@ -34,7 +34,7 @@ def test_exports_every_declared_symbol(lib):
 
 
 def test_abi_version_and_struct_sizes(lib):
-    assert lib.cmb_abi_version() == 2
+    assert lib.cmb_abi_version() == 3
     assert ctypes.sizeof(coverm_b200.ContigStats) == 144
     assert ctypes.sizeof(coverm_b200.Params) == 56
     assert ctypes.sizeof(coverm_b200.ReadBatch) == 8 + 13 * 8
