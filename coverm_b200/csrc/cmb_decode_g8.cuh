@@ -301,7 +301,9 @@ __global__ void __launch_bounds__(G8_WARPS * 32, 2) kd_inflate_g8(const InflateA
     const uint8_t* in = a.comp + (have ? a.coff[b] : 0);
     const uint32_t in_len = have ? a.clen[b] : 0;
     const uint8_t* const in_end = in + in_len;
-    uint8_t* const out = a.out + (have ? a.uoff[b] : 0);
+    // an idle stream still issues the rotated loop's unconditional loads: give it a real address (a.out is a biased base
+    // pointer -- only a.out + uoff[b] of a block in range is backed by memory)
+    uint8_t* const out = a.out + a.uoff[have ? b : a.b0];
     uint32_t st = (have && !arrived) ? 31u : 0u;  // 0 = fine so far; otherwise the check that declined the block
     uint32_t op = 0;
     G8Reader br;

@@ -36,6 +36,9 @@
 #include <cstring>
 #include <atomic>
 #include <chrono>
+#include <condition_variable>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <thread>
 #include <vector>
@@ -53,6 +56,7 @@ namespace {
 #include "cmb_k3.cuh"
 #include "cmb_decode.cuh"
 #include "cmb_decode_g8.cuh"
+#include "cmb_decode_t1.cuh"
 
 // rows[i].hist_offset += base for the rows that carry histogram pairs (cmb_allgather_stats: local -> global pair offsets)
 __global__ void __launch_bounds__(256) k_rebase_hist_offsets(cmb_contig_stats* rows, uint32_t n, uint64_t base) {
@@ -66,6 +70,28 @@ typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_
                                     CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 std::string g_create_error;
+
+// Ranks that live in ONE process (cmb_comm_init_local) meet here before every collective: a rank must not be inside a CUDA call
+// that synchronises across devices (cudaHostAlloc, cudaMalloc, cudaFree ...) while another rank's NCCL kernel is already
+// waiting for it -- that is the classic single-process multi-GPU deadlock.  All allocation happens before the barrier, only
+// stream-ordered work after it.
+struct LocalBarrier {
+  std::mutex m;
+  std::condition_variable cv;
+  int n = 0, waiting = 0;
+  uint64_t generation = 0;
+  void arrive_and_wait() {
+    std::unique_lock<std::mutex> lk(m);
+    const uint64_t g = generation;
+    if (++waiting == n) {
+      waiting = 0;
+      ++generation;
+      cv.notify_all();
+    } else {
+      cv.wait(lk, [&] { return generation != g; });
+    }
+  }
+};
 
 struct DevBatch {  // device mirror of one staging batch
   void* slab = nullptr;
@@ -103,6 +129,7 @@ struct cmb_ctx {
   // multi-GPU (cmb_comm_*): one NCCL communicator per ctx, collectives on the ctx stream
   ncclComm_t comm = nullptr;
   int comm_rank = 0, comm_size = 1;
+  std::shared_ptr<LocalBarrier> local_barrier;  // set when all ranks of the communicator live in this process
   uint8_t* d_xchg = nullptr;  // staging of cmb_comm_allgather
   size_t xchg_cap = 0;
   cmb_hist_pair* d_pairs_all = nullptr;  // concatenated histogram pairs of all ranks (cmb_allgather_stats)
@@ -787,7 +814,10 @@ int cmb_comm_init_local(cmb_ctx* const* ctxs, int n_ranks) {
   }
   std::vector<ncclComm_t> comms(n_ranks);
   NCCL_TRY(ctxs[0], ncclCommInitAll(comms.data(), n_ranks, devs.data()));
+  auto barrier = std::make_shared<LocalBarrier>();
+  barrier->n = n_ranks;
   for (int r = 0; r < n_ranks; ++r) {
+    ctxs[r]->local_barrier = barrier;
     ctxs[r]->comm = comms[r];
     ctxs[r]->comm_rank = r;
     ctxs[r]->comm_size = n_ranks;
@@ -801,6 +831,7 @@ void cmb_comm_destroy(cmb_ctx* c) {
   if (c->stream) cudaStreamSynchronize(c->stream);
   ncclCommDestroy(c->comm);
   c->comm = nullptr;
+  c->local_barrier.reset();
   c->comm_rank = 0;
   c->comm_size = 1;
 }
@@ -819,6 +850,7 @@ int cmb_comm_allgather(cmb_ctx* c, const void* send, void* recv, size_t bytes) {
   }
   uint8_t* d_send = c->d_xchg;
   uint8_t* d_recv = c->d_xchg + bytes;
+  if (c->local_barrier) c->local_barrier->arrive_and_wait();
   CU_TRY(c, cudaMemcpyAsync(d_send, send, bytes, cudaMemcpyHostToDevice, c->stream));
   NCCL_TRY(c, ncclAllGather(d_send, d_recv, bytes, ncclChar, c->comm, c->stream));
   CU_TRY(c, cudaMemcpyAsync(recv, d_recv, bytes * (size_t)c->comm_size, cudaMemcpyDeviceToHost, c->stream));
@@ -854,6 +886,7 @@ int cmb_allgather_stats(cmb_ctx* c, const uint32_t* tid_cuts, const uint64_t* pa
       CU_TRY(c, cudaGetLastError());
     }
   }
+  if (c->local_barrier) c->local_barrier->arrive_and_wait();
   // every rank broadcasts its own row range in place: afterwards each rank's table is complete (an all-gather with ragged counts)
   NCCL_TRY(c, ncclGroupStart());
   for (int r = 0; r < N; ++r) {
@@ -912,12 +945,25 @@ constexpr size_t DEC_SLACK = 1024;
 constexpr size_t DEC_FRONT = 256;              // readable bytes in front of the first uploaded block (the bit readers align down)
 constexpr uint64_t DEC_TAIL_BYTES = 4u << 20;  // ranged decode: inflated bytes kept beyond the range for its last straddling record
 
-// Launch the inflate kernel over blocks [a.b0, a.b1): the four-streams-per-warp variant unless CMB_INFLATE_G8=0.
-int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool allow_g8 = true) {
-  static const bool g8_default = !(getenv("CMB_INFLATE_G8") && getenv("CMB_INFLATE_G8")[0] == '0');
-  const bool g8 = g8_default && allow_g8 && !a.block_list;
+// Launch the inflate kernel over blocks [a.b0, a.b1).  CMB_INFLATE selects the first-pass kernel: t1 (default: one thread
+// per block + kd_crc32), g8 (four blocks per warp) or w1 (one block per warp, also the second pass over declined blocks).
+int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first_pass = true) {
+  static const int which = [] {
+    const char* e = getenv("CMB_INFLATE");
+    if (e && !strcmp(e, "g8")) return 1;
+    if (e && !strcmp(e, "w1")) return 2;
+    if (getenv("CMB_INFLATE_G8") && getenv("CMB_INFLATE_G8")[0] == '0') return 2;
+    return 0;
+  }();
+  const int k = (first_pass && !a.block_list) ? which : 2;
   const uint32_t nb = a.b1 - a.b0;
-  if (g8) {
+  if (k == 0) {
+    CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
+    const uint32_t grid = std::min<uint32_t>((nb + T1_THREADS - 1) / T1_THREADS, (uint32_t)c->sm_count * 2);
+    kd_inflate_t1<<<grid, T1_THREADS, T1_SMEM_BYTES, st>>>(a);
+    CU_TRY(c, cudaGetLastError());
+    kd_crc32<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)c->sm_count * 8), 256, 0, st>>>(a);
+  } else if (k == 1) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_g8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM_BYTES));
     const uint32_t per_cta = G8_WARPS * G8_STREAMS;
     const uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, (uint32_t)c->sm_count * 2);

@@ -87,10 +87,11 @@ class BlockRangeFinder {
       return cache_[b].state == 1;
     }
     if (cache_.size() < nb_) cache_.resize(nb_);
-    // inflate b and enough of what follows to test six consecutive headers (records may be large)
+    // inflate b and a little of what follows, enough to test six consecutive headers of ordinary records (a chain that runs
+    // off the inflated data counts as confirmed, like in the host decoder)
     uint32_t e = b + 1;
     uint64_t have = bx_.blocks[b].isize;
-    while (e < nb_ && have < bx_.blocks[b].isize + (1u << 20)) have += bx_.blocks[e++].isize;
+    while (e < nb_ && e < b + 3 && have < bx_.blocks[b].isize + (64u << 10)) have += bx_.blocks[e++].isize;
     buf_.resize((size_t)have + 8);
     bx_.inflate(b, e, buf_.data(), inf_);
     probes_ += e - b;
