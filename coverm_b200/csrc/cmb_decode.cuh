@@ -62,6 +62,7 @@ struct InflateArgs {
   const uint32_t* ready;
   // optional indirection: ticket t in [b0, b1) names block block_list[t] (second pass over the blocks the first declined)
   const uint32_t* block_list;
+  uint8_t* scratch;  // kd_inflate_t1: 160 bytes per BGZF block (indexed by block number)
 };
 
 // The compressed stream seen through a 64-bit bit buffer; words come from a per-lane register window.

@@ -14,23 +14,24 @@
 // declined block gets the one-stream-per-warp kernel and finally the library's zlib.
 #pragma once
 
-constexpr uint32_t T1_THREADS = 128;  // per CTA; two CTAs per SM
+constexpr uint32_t T1_THREADS = 128;  // per CTA; four CTAs per SM (452 B of tables per thread)
 
-struct T1Stream {           // per-thread tables; 217 words: an odd stride keeps the 32 lanes of a warp on 32 different banks
-  uint16_t perm_lit[288];   // literal/length symbols sorted by (code length, symbol)
-  int16_t base_lit[16];     // index of the first symbol of length L in perm minus the first code of length L
+struct T1Stream {           // per-thread tables; 113 words: an odd stride keeps the 32 lanes of a warp on 32 different banks
+  uint8_t perm_lit_lo[288];  // literal/length symbols sorted by (code length, symbol): low 8 bits ...
+  uint32_t perm_lit_hi[9];   // ... and bit 8 (symbol >= 256: end-of-block / length codes), one bit per entry
+  int16_t base_lit[16];      // index of the first symbol of length L in perm minus the first code of length L
   int16_t base_dst[16];
-  uint16_t tmp[16];         // counts / fill cursors while a table is built
-  uint8_t perm_dst[32];     // distance symbols (and, while a dynamic header is read, the code-length code's symbols)
-  uint8_t lens4[160];       // code lengths of the block being set up, 4 bits each (literal/length then distance)
-  uint16_t pad[2];
+  uint16_t tmp[16];          // counts / fill cursors while a table is built
+  uint8_t perm_dst[32];      // distance symbols (and, while a dynamic header is read, the code-length code's symbols)
 };
-static_assert(sizeof(T1Stream) == 868, "T1Stream layout");
+static_assert(sizeof(T1Stream) == 452, "T1Stream layout");
 constexpr uint32_t T1_SMEM_BYTES = T1_THREADS * sizeof(T1Stream);
+constexpr uint32_t T1_LENS_BYTES = 160;  // code lengths of the deflate block being set up, 4 bits each: global scratch per BGZF
+                                         // block (InflateArgs::scratch), so they cost no shared memory
 
-struct T1Reader {  // LSB-first bit reader over global memory; one aligned word is always prefetched
-  const uint32_t* wp;  // the word after w_next
-  uint32_t w_next;
+struct T1Reader {  // LSB-first bit reader over global memory; two aligned words are always in flight ahead of the buffer
+  const uint32_t* wp;  // the word after w1
+  uint32_t w0, w1;     // the next two words of the stream
   uint64_t buf;
   uint32_t cnt;
   __device__ __forceinline__ void init(const uint8_t* p) {
@@ -39,14 +40,16 @@ struct T1Reader {  // LSB-first bit reader over global memory; one aligned word 
     const uint32_t skip = (uint32_t)(a & 3) * 8;
     buf = (uint64_t)(__ldcg(wp++) >> skip);  // L2 only: the copy engine may still be writing neighbouring blocks
     cnt = 32 - skip;
-    w_next = __ldcg(wp++);
+    w0 = __ldcg(wp++);
+    w1 = __ldcg(wp++);
     refill();
   }
   __device__ __forceinline__ void refill() {  // afterwards cnt >= 33
     if (cnt <= 32) {
-      buf |= (uint64_t)w_next << cnt;
+      buf |= (uint64_t)w0 << cnt;
       cnt += 32;
-      w_next = __ldcg(wp++);
+      w0 = w1;
+      w1 = __ldcg(wp++);
     }
   }
   __device__ __forceinline__ void consume(uint32_t n) {
@@ -55,8 +58,8 @@ struct T1Reader {  // LSB-first bit reader over global memory; one aligned word 
   }
   __device__ __forceinline__ uint32_t bits(uint32_t n) const { return (uint32_t)buf & ((1u << n) - 1); }
   __device__ __forceinline__ uint32_t peek15() const { return __brev((uint32_t)buf) >> 17; }  // next 15 bits, first bit on top
-  // first byte boundary at or after the read position (w_next's word starts at wp - 1; cnt unread bits precede it)
-  __device__ __forceinline__ const uint8_t* byte_pos_ceil() const { return reinterpret_cast<const uint8_t*>(wp - 1) - (cnt >> 3); }
+  // first byte boundary at or after the read position (w0's word starts at wp - 2; cnt unread bits precede it)
+  __device__ __forceinline__ const uint8_t* byte_pos_ceil() const { return reinterpret_cast<const uint8_t*>(wp - 2) - (cnt >> 3); }
 };
 
 // Length of the code at the top of `p` (15 bits, MSB first): 1 + the number of limits <= p.  16 = not a code of this table.
@@ -67,10 +70,11 @@ __device__ __forceinline__ uint32_t t1_code_len(uint32_t p, const uint32_t (&lim
   return L;
 }
 
-// Canonical Huffman table from n code lengths (`len_of(s)`, 0 = unused): perm, base[1..15] and the fifteen limits.
+// Canonical Huffman table from n code lengths (`len_of(s)`, 0 = unused): perm (through `put(index, symbol)`), base[1..15]
+// and the fifteen limits.
 // Returns false for an over-subscribed set.
-template <class Perm, class LenOf>
-__device__ __forceinline__ bool t1_build(LenOf len_of, uint32_t n, Perm* perm, int16_t* base, uint16_t* tmp, uint32_t (&lim)[15]) {
+template <class LenOf, class Put>
+__device__ __forceinline__ bool t1_build(LenOf len_of, uint32_t n, Put put, int16_t* base, uint16_t* tmp, uint32_t (&lim)[15]) {
 #pragma unroll
   for (int L = 0; L < 16; ++L) tmp[L] = 0;
   for (uint32_t s = 0; s < n; ++s) tmp[len_of(s)] += 1;
@@ -94,12 +98,12 @@ __device__ __forceinline__ bool t1_build(LenOf len_of, uint32_t n, Perm* perm, i
   }
   for (uint32_t s = 0; s < n; ++s) {
     const uint32_t l = len_of(s);
-    if (l) perm[tmp[l]++] = (Perm)s;
+    if (l) put((uint32_t)tmp[l]++, s);
   }
   return ok;
 }
 
-__global__ void __launch_bounds__(T1_THREADS, 2) kd_inflate_t1(const InflateArgs a) {
+__global__ void __launch_bounds__(T1_THREADS, 4) kd_inflate_t1(const InflateArgs a) {
   extern __shared__ __align__(16) uint8_t t1_smem[];
   T1Stream& S = reinterpret_cast<T1Stream*>(t1_smem)[threadIdx.x];
   uint32_t lit_lim[15], dst_lim[15];
@@ -107,7 +111,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) kd_inflate_t1(const InflateArgs
   for (int k = 0; k < 15; ++k) lit_lim[k] = dst_lim[k] = 0;
   T1Reader br;
   br.wp = nullptr;
-  br.w_next = 0;
+  br.w0 = br.w1 = 0;
   br.buf = 0;
   br.cnt = 0;
 
@@ -176,12 +180,13 @@ __global__ void __launch_bounds__(T1_THREADS, 2) kd_inflate_t1(const InflateArgs
         }
         if (st == 0 && bfinal) state = FIN;  // finished: verdict below
       } else if (st == 0) {
+        uint8_t* const l4 = a.scratch + (size_t)b * T1_LENS_BYTES;  // this BGZF block's code-length scratch
         uint32_t hlit = 288, hdist = 32;
         if (btype == 1) {  // fixed code lengths (RFC 1951 3.2.6)
           for (uint32_t i = 0; i < 160; ++i) {
             const uint32_t s0 = 2 * i, s1 = 2 * i + 1;
             auto fl = [](uint32_t s) -> uint32_t { return s < 144 ? 8u : s < 256 ? 9u : s < 280 ? 7u : s < 288 ? 8u : 5u; };
-            S.lens4[i] = (uint8_t)(fl(s0) | (fl(s1) << 4));
+            l4[i] = (uint8_t)(fl(s0) | (fl(s1) << 4));
           }
         } else {  // dynamic: HLIT, HDIST, HCLEN, the code-length code, then the run-length coded lengths
           br.refill();
@@ -191,17 +196,17 @@ __global__ void __launch_bounds__(T1_THREADS, 2) kd_inflate_t1(const InflateArgs
           br.consume(14);
           if (hlit > 286 || hdist > 30) st = 5;
           if (st == 0) {
-            // code-length code: 19 lengths of 3 bits, kept in the first 10 bytes of lens4 while its table is built
-            for (uint32_t i = 0; i < 10; ++i) S.lens4[150 + i] = 0;
+            // code-length code: 19 lengths of 3 bits, kept in the last 10 bytes of the scratch while its table is built
+            for (uint32_t i = 0; i < 10; ++i) l4[150 + i] = 0;
             for (uint32_t i = 0; i < hclen; ++i) {
               br.refill();
               const uint32_t sym = c_clen_order[i], v = br.bits(3);
               br.consume(3);
-              S.lens4[150 + (sym >> 1)] |= (uint8_t)(v << ((sym & 1) * 4));
+              l4[150 + (sym >> 1)] |= (uint8_t)(v << ((sym & 1) * 4));
             }
-            uint8_t* l4 = S.lens4;
-            const bool okc = t1_build<uint8_t>([l4](uint32_t s) -> uint32_t { return (l4[150 + (s >> 1)] >> ((s & 1) * 4)) & 15u; }, 19u, S.perm_dst, S.base_dst,
-                                               S.tmp, dst_lim);
+            uint8_t* pd = S.perm_dst;
+            const bool okc = t1_build([l4](uint32_t s) -> uint32_t { return (l4[150 + (s >> 1)] >> ((s & 1) * 4)) & 15u; }, 19u,
+                                      [pd](uint32_t i, uint32_t s) { pd[i] = (uint8_t)s; }, S.base_dst, S.tmp, dst_lim);
             if (!okc) st = 6;
           }
           if (st == 0) {
@@ -209,7 +214,7 @@ __global__ void __launch_bounds__(T1_THREADS, 2) kd_inflate_t1(const InflateArgs
             uint32_t n = 0, prev = 0;
             auto put = [&](uint32_t i, uint32_t v) {
               const uint32_t sh = (i & 1) * 4;
-              S.lens4[i >> 1] = (uint8_t)((S.lens4[i >> 1] & ~(15u << sh)) | (v << sh));
+              l4[i >> 1] = (uint8_t)((l4[i >> 1] & ~(15u << sh)) | (v << sh));
             };
             while (n < total && st == 0) {
               br.refill();
@@ -251,16 +256,24 @@ __global__ void __launch_bounds__(T1_THREADS, 2) kd_inflate_t1(const InflateArgs
                 n += rep;
               }
             }
-            if (st == 0 && ((S.lens4[128] & 15u) == 0)) st = 10;  // no end-of-block code (symbol 256)
+            if (st == 0 && ((l4[128] & 15u) == 0)) st = 10;  // no end-of-block code (symbol 256)
           }
         }
         if (st == 0) {
-          uint8_t* l4 = S.lens4;
           const uint32_t hl = hlit;
-          const bool okd = t1_build<uint8_t>([l4, hl](uint32_t s) -> uint32_t { const uint32_t i = hl + s; return (l4[i >> 1] >> ((i & 1) * 4)) & 15u; }, hdist,
-                                             S.perm_dst, S.base_dst, S.tmp, dst_lim);
-          const bool okl = t1_build<uint16_t>([l4](uint32_t s) -> uint32_t { return (l4[s >> 1] >> ((s & 1) * 4)) & 15u; }, hlit, S.perm_lit, S.base_lit, S.tmp,
-                                              lit_lim);
+          uint8_t* pd = S.perm_dst;
+          uint8_t* plo = S.perm_lit_lo;
+          uint32_t* phi = S.perm_lit_hi;
+#pragma unroll
+          for (int k = 0; k < 9; ++k) phi[k] = 0;
+          const bool okd = t1_build([l4, hl](uint32_t s) -> uint32_t { const uint32_t i = hl + s; return (l4[i >> 1] >> ((i & 1) * 4)) & 15u; }, hdist,
+                                    [pd](uint32_t i, uint32_t s) { pd[i] = (uint8_t)s; }, S.base_dst, S.tmp, dst_lim);
+          const bool okl = t1_build([l4](uint32_t s) -> uint32_t { return (l4[s >> 1] >> ((s & 1) * 4)) & 15u; }, hlit,
+                                    [plo, phi](uint32_t i, uint32_t s) {
+                                      plo[i] = (uint8_t)s;
+                                      if (s & 256u) phi[i >> 5] |= 1u << (i & 31);
+                                    },
+                                    S.base_lit, S.tmp, lit_lim);
           if (!okd) st = 11;
           else if (!okl) st = 12;
           else state = SYM;
@@ -280,7 +293,8 @@ __global__ void __launch_bounds__(T1_THREADS, 2) kd_inflate_t1(const InflateArgs
           st = 13;
           break;
         }
-        const uint32_t sym = S.perm_lit[(int)S.base_lit[L] + (int)(p >> (15 - L))];
+        const uint32_t li = (uint32_t)((int)S.base_lit[L] + (int)(p >> (15 - L)));
+        const uint32_t sym = (uint32_t)S.perm_lit_lo[li] | (((S.perm_lit_hi[li >> 5] >> (li & 31)) & 1u) << 8);
         br.consume(L);
         if (sym < 256) {
           if (op >= n_out) {
@@ -335,7 +349,19 @@ __global__ void __launch_bounds__(T1_THREADS, 2) kd_inflate_t1(const InflateArgs
         }
         uint8_t* dp = out + op;
         const uint8_t* sp = dp - dist;
-        for (uint32_t i = 0; i < len; ++i) dp[i] = sp[i];  // byte by byte: an overlapping copy replicates its own output
+        if (dist >= len) {  // source and destination do not overlap: eight loads in flight, then eight stores
+          for (uint32_t i = 0; i < len; i += 8) {
+            uint8_t t8[8];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k)
+              if (i + k < len) t8[k] = sp[i + k];
+#pragma unroll
+            for (uint32_t k = 0; k < 8; ++k)
+              if (i + k < len) dp[i + k] = t8[k];
+          }
+        } else {
+          for (uint32_t i = 0; i < len; ++i) dp[i] = sp[i];  // byte by byte: an overlapping copy replicates its own output
+        }
         op += len;
       }
     }

@@ -57,6 +57,7 @@ namespace {
 #include "cmb_decode.cuh"
 #include "cmb_decode_g8.cuh"
 #include "cmb_decode_t1.cuh"
+#include "cmb_pairs.cuh"
 
 // rows[i].hist_offset += base for the rows that carry histogram pairs (cmb_allgather_stats: local -> global pair offsets)
 __global__ void __launch_bounds__(256) k_rebase_hist_offsets(cmb_contig_stats* rows, uint32_t n, uint64_t base) {
@@ -143,6 +144,8 @@ struct cmb_ctx {
   cmb_hist_pair* d_pairs = nullptr;
   uint64_t pair_capacity = 0;
   int2* d_block_minmax = nullptr;
+  int2* d_block_xrange = nullptr;  // same capacity as d_block_minmax
+  bool have_xrange = false;
   uint32_t block_minmax_capacity = 0, block_minmax_used = 0;
   CUtensorMap tmap{};
   bool arena_dirty = true;
@@ -166,6 +169,7 @@ struct cmb_ctx {
     uint64_t *d_coff = nullptr, *d_ustart = nullptr, *d_guess = nullptr, *d_exit = nullptr, *d_rec_base = nullptr, *d_cig_base = nullptr;
     uint32_t *d_clen = nullptr, *d_isize = nullptr, *d_status = nullptr, *d_nrec = nullptr, *d_ncig = nullptr, *d_dirty = nullptr;
     size_t blocks_cap = 0;
+    uint8_t* d_t1_scratch = nullptr;  // kd_inflate_t1: code-length scratch, 160 B per block
     uint32_t* d_tickets = nullptr;  // [0] block ticket, [1 + w] window w has arrived
     size_t tickets_cap = 0;
     uint32_t* d_block_window = nullptr;
@@ -178,9 +182,21 @@ struct cmb_ctx {
     size_t tuple_slab_bytes = 0;
     uint32_t last_n_rec = 0, last_n_cig = 0;  // tuples of the last successful cmb_submit_bgzf (cmb_last_bgzf_batch)
     bool last_valid = false;
+    // mate matching (cmb_pairs.cuh)
+    uint64_t* d_pair_key = nullptr;
+    int32_t* d_pair_mate = nullptr;
+    uint32_t* d_pair_next = nullptr;
+    size_t pair_rec_cap = 0;
+    unsigned long long* d_pair_tag = nullptr;
+    uint32_t* d_pair_head = nullptr;
+    size_t pair_table_cap = 0;
+    const int32_t* last_mate = nullptr;
     std::vector<void*> pinned;
     std::vector<cudaStream_t> streams;
     std::vector<cudaEvent_t> slot_events, done_events;
+    std::vector<cudaStream_t> cstreams;      // per-window inflate launches (CMB_INFLATE=t1): kernels of different windows overlap
+    std::vector<cudaEvent_t> window_events;  // window w has been copied
+    std::vector<cudaEvent_t> cstream_done;
     cudaEvent_t ev[6]{};
     bool have_events = false;
   } dec;
@@ -278,19 +294,25 @@ void free_reference(cmb_ctx* c) {
   c->pair_capacity = 0;
 }
 
-int launch_k1(cmb_ctx* c, const cmb_read_batch& b, uint32_t n_records, uint32_t n_intervals, uint32_t excl_n = 0xffffffffu) {
+int launch_k1(cmb_ctx* c, const cmb_read_batch& b, uint32_t n_records, uint32_t n_intervals, uint32_t excl_n = 0xffffffffu,
+              const int32_t* mate = nullptr) {
   if (n_records == 0) return CMB_OK;
   const uint32_t blocks = (n_records + K1_THREADS - 1) / K1_THREADS;
   if (c->block_minmax_used + blocks > c->block_minmax_capacity) {
     // grow (rare): allocate a larger array and copy what is there
     uint32_t ncap = std::max(c->block_minmax_capacity * 2, c->block_minmax_used + blocks + 4096);
-    int2* nd = nullptr;
+    int2 *nd = nullptr, *nx = nullptr;
     CU_TRY(c, cudaMalloc(&nd, sizeof(int2) * (size_t)ncap));
-    if (c->block_minmax_used)
+    CU_TRY(c, cudaMalloc(&nx, sizeof(int2) * (size_t)ncap));
+    if (c->block_minmax_used) {
       CU_TRY(c, cudaMemcpyAsync(nd, c->d_block_minmax, sizeof(int2) * (size_t)c->block_minmax_used, cudaMemcpyDeviceToDevice, c->stream));
+      CU_TRY(c, cudaMemcpyAsync(nx, c->d_block_xrange, sizeof(int2) * (size_t)c->block_minmax_used, cudaMemcpyDeviceToDevice, c->stream));
+    }
     CU_TRY(c, cudaStreamSynchronize(c->stream));
     cudaFree(c->d_block_minmax);
+    cudaFree(c->d_block_xrange);
     c->d_block_minmax = nd;
+    c->d_block_xrange = nx;
     c->block_minmax_capacity = ncap;
   }
   K1Args a{};
@@ -303,8 +325,10 @@ int launch_k1(cmb_ctx* c, const cmb_read_batch& b, uint32_t n_records, uint32_t 
   a.arena = c->d_arena; a.tail_sum = c->d_tail_sum; a.rows = c->d_rows;
   a.block_minmax = c->d_block_minmax + c->block_minmax_used;
   a.error_flags = c->d_counters + 0;
-  a.kept_range = c->d_counters + 6;
+  a.block_xrange = c->comm_size > 1 || excl_n != 0xffffffffu ? c->d_block_xrange + c->block_minmax_used : nullptr;
   a.excl_n = excl_n;
+  if (a.block_xrange) c->have_xrange = true;
+  a.mate = mate;
   a.p = c->params;
   a.filter_single = c->mode.filter_single_reads;
   a.filter_pairs = c->mode.filter_pairs;
@@ -346,7 +370,8 @@ int run_end_of_sample(cmb_ctx* c) {
   const uint32_t excl = (uint32_t)std::min<uint64_t>(c->params.contig_end_exclusion, 0x7fffffffu);
   CU_TRY(c, cudaEventRecord(c->ev[2], c->stream));
   if (c->block_minmax_used) {
-    k1c_check_sorted<<<1, 1024, 0, c->stream>>>(c->d_block_minmax, c->block_minmax_used, c->d_counters + 0);
+    k1c_check_sorted<<<1, 1024, 0, c->stream>>>(c->d_block_minmax, c->block_minmax_used, c->d_counters + 0,
+                                                c->have_xrange ? c->d_block_xrange : nullptr, c->d_counters + 6);
     CU_TRY(c, cudaGetLastError());
   }
   {
@@ -494,6 +519,7 @@ int cmb_create(const cmb_device_cfg* cfg, cmb_ctx** out) {
   CREATE_TRY(cudaMemset(c->d_counters, 0, 64));
   c->block_minmax_capacity = 1u << 16;
   CREATE_TRY(cudaMalloc(&c->d_block_minmax, sizeof(int2) * (size_t)c->block_minmax_capacity));
+  CREATE_TRY(cudaMalloc(&c->d_block_xrange, sizeof(int2) * (size_t)c->block_minmax_capacity));
   const char* env = getenv("CMB_CLEAN_AS_YOU_GO");
   if (env && env[0] == '0') c->clean_as_you_go = false;
   *out = c;
@@ -516,6 +542,7 @@ void cmb_destroy(cmb_ctx* c) {
     if (e) cudaEventDestroy(e);
   cudaFree(c->d_counters);
   cudaFree(c->d_block_minmax);
+  cudaFree(c->d_block_xrange);
   cmb_comm_destroy(c);
   cudaFree(c->d_xchg);
   cudaFree(c->d_pairs_all);
@@ -523,11 +550,15 @@ void cmb_destroy(cmb_ctx* c) {
     auto& d = c->dec;
     cudaFree(d.d_comp); cudaFree(d.d_inflated); cudaFree(d.d_coff); cudaFree(d.d_ustart); cudaFree(d.d_guess); cudaFree(d.d_exit);
     cudaFree(d.d_rec_base); cudaFree(d.d_cig_base); cudaFree(d.d_clen); cudaFree(d.d_isize); cudaFree(d.d_status); cudaFree(d.d_nrec);
-    cudaFree(d.d_ncig); cudaFree(d.d_dirty); cudaFree(d.d_tickets); cudaFree(d.d_block_window); if (d.h_ones) cudaFreeHost(d.h_ones); cudaFree(d.d_cnt); cudaFree(d.d_rec_off); cudaFree(d.d_tuple_slab);
+    cudaFree(d.d_pair_key); cudaFree(d.d_pair_mate); cudaFree(d.d_pair_next); cudaFree(d.d_pair_tag); cudaFree(d.d_pair_head);
+    cudaFree(d.d_ncig); cudaFree(d.d_dirty); cudaFree(d.d_tickets); cudaFree(d.d_t1_scratch); cudaFree(d.d_block_window); if (d.h_ones) cudaFreeHost(d.h_ones); cudaFree(d.d_cnt); cudaFree(d.d_rec_off); cudaFree(d.d_tuple_slab);
     for (auto p : d.pinned) cudaFreeHost(p);
     for (auto st : d.streams) cudaStreamDestroy(st);
     for (auto e : d.slot_events) cudaEventDestroy(e);
     for (auto e : d.done_events) cudaEventDestroy(e);
+    for (auto st : d.cstreams) cudaStreamDestroy(st);
+    for (auto e : d.window_events) cudaEventDestroy(e);
+    for (auto e : d.cstream_done) cudaEventDestroy(e);
     if (d.have_events)
       for (auto e : d.ev) cudaEventDestroy(e);
   }
@@ -631,6 +662,7 @@ int cmb_begin_sample(cmb_ctx* c) {
   c->timing = cmb_sample_timing{};
   c->k1_events_used = 0;
   c->block_minmax_used = 0;
+  c->have_xrange = false;
   c->n_records = c->n_intervals = 0;
   CU_TRY(c, cudaEventRecord(c->ev[0], c->stream));
   if (c->n_local) {
@@ -712,7 +744,10 @@ int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* dev, uint32_t n_re
   if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_submit_device_batch: no sample in progress");
   if (c->n_local == 0) return CMB_OK;
   CU_TRY(c, cudaSetDevice(c->device));
-  return launch_k1(c, *dev, n_records, n_intervals);
+  // re-submitting the tuples of the last device decode (cmb_last_bgzf_batch) in pair mode: its mate table goes with it
+  const int32_t* mate = (c->dec.last_valid && c->dec.last_mate && (const void*)dev->tid == c->dec.d_tuple_slab && c->mode.filter_pairs)
+                            ? c->dec.last_mate : nullptr;
+  return launch_k1(c, *dev, n_records, n_intervals, 0xffffffffu, mate);
 }
 
 int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** dev_stats) {
@@ -947,7 +982,7 @@ constexpr uint64_t DEC_TAIL_BYTES = 4u << 20;  // ranged decode: inflated bytes 
 
 // Launch the inflate kernel over blocks [a.b0, a.b1).  CMB_INFLATE selects the first-pass kernel: t1 (default: one thread
 // per block + kd_crc32), g8 (four blocks per warp) or w1 (one block per warp, also the second pass over declined blocks).
-int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first_pass = true) {
+int inflate_kind() {  // CMB_INFLATE: t1 (default) | g8 | w1
   static const int which = [] {
     const char* e = getenv("CMB_INFLATE");
     if (e && !strcmp(e, "g8")) return 1;
@@ -955,11 +990,21 @@ int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first
     if (getenv("CMB_INFLATE_G8") && getenv("CMB_INFLATE_G8")[0] == '0') return 2;
     return 0;
   }();
+  return which;
+}
+// t1 only: one launch per copied window, stream-ordered behind the window's copy (no device-side waiting for data).
+// CMB_INFLATE_PERSISTENT=1 selects the single persistent launch whose threads poll the windows' arrival flags instead.
+bool inflate_per_window() {
+  static const bool v = inflate_kind() == 0 && !(getenv("CMB_INFLATE_PERSISTENT") && getenv("CMB_INFLATE_PERSISTENT")[0] == '1');
+  return v;
+}
+int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first_pass = true) {
+  const int which = inflate_kind();
   const int k = (first_pass && !a.block_list) ? which : 2;
   const uint32_t nb = a.b1 - a.b0;
   if (k == 0) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
-    const uint32_t grid = std::min<uint32_t>((nb + T1_THREADS - 1) / T1_THREADS, (uint32_t)c->sm_count * 2);
+    const uint32_t grid = std::min<uint32_t>((nb + T1_THREADS - 1) / T1_THREADS, (uint32_t)c->sm_count * 4);
     kd_inflate_t1<<<grid, T1_THREADS, T1_SMEM_BYTES, st>>>(a);
     CU_TRY(c, cudaGetLastError());
     kd_crc32<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)c->sm_count * 8), 256, 0, st>>>(a);
@@ -1024,7 +1069,6 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     return fail(c, CMB_E_ARG, "cmb_submit_bgzf: null argument");
   if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: no sample in progress");
   if (c->n_acquired) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: a staging batch is still acquired");
-  if (c->mode.filter_pairs) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: pair filtering needs host mate matching");
   *out = cmb_bgzf_result{};
   const uint32_t nb = in->n_blocks;
   if (nb == 0) return CMB_OK;
@@ -1079,6 +1123,9 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     CU_TRY(c, cudaMalloc(&d.d_exit, 8 * want)); CU_TRY(c, cudaMalloc(&d.d_rec_base, 8 * want)); CU_TRY(c, cudaMalloc(&d.d_cig_base, 8 * want));
     CU_TRY(c, cudaMalloc(&d.d_clen, 4 * want)); CU_TRY(c, cudaMalloc(&d.d_isize, 4 * want)); CU_TRY(c, cudaMalloc(&d.d_status, 4 * want));
     CU_TRY(c, cudaMalloc(&d.d_nrec, 4 * want)); CU_TRY(c, cudaMalloc(&d.d_ncig, 4 * want)); CU_TRY(c, cudaMalloc(&d.d_dirty, 4 * want));
+    cudaFree(d.d_t1_scratch);
+    d.d_t1_scratch = nullptr;
+    CU_TRY(c, cudaMalloc(&d.d_t1_scratch, (size_t)T1_LENS_BYTES * want));
     d.blocks_cap = want;
   }
   if (!d.d_cnt) CU_TRY(c, cudaMalloc(&d.d_cnt, 64));
@@ -1158,9 +1205,27 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
   CU_TRY(c, cudaMemsetAsync(d.d_comp, 0, DEC_FRONT, c->stream));
   CU_TRY(c, cudaEventRecord(d.ev[1], c->stream));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(d.streams[t], d.ev[1], 0));
-  {  // one persistent launch over every block; its warps wait for their block's window to arrive
+  const bool per_window = inflate_per_window();
+  const uint32_t NCS = 64;  // compute streams for the per-window launches
+  if (per_window) {
+    CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
+    while (d.cstreams.size() < std::min<size_t>(NCS, windows.size())) {
+      cudaStream_t cs;
+      CU_TRY(c, cudaStreamCreateWithFlags(&cs, cudaStreamNonBlocking));
+      d.cstreams.push_back(cs);
+      cudaEvent_t e;
+      CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      d.cstream_done.push_back(e);
+    }
+    while (d.window_events.size() < windows.size()) {
+      cudaEvent_t e;
+      CU_TRY(c, cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+      d.window_events.push_back(e);
+    }
+    for (size_t k = 0; k < std::min<size_t>(NCS, windows.size()); ++k) CU_TRY(c, cudaStreamWaitEvent(d.cstreams[k], d.ev[1], 0));
+  } else {  // one persistent launch over every block; its warps wait for their block's window to arrive
     InflateArgs a{};
-    a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
+    a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart; a.scratch = d.d_t1_scratch;
     // blocks before the one holding the first record are header text the host has already read: not inflated here
     a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
     a.block_window = d.d_block_window; a.ready = d.d_tickets + 1;
@@ -1198,7 +1263,22 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
           slot ^= 1;
         }
       }
-      if (!check(cudaMemcpyAsync(d.d_tickets + 1 + w, d.h_ones, 4, cudaMemcpyHostToDevice, st))) break;  // window w has arrived
+      if (per_window) {
+        // the window's blocks are inflated by their own launch, ordered behind the copy by an event; many windows' launches
+        // are in flight at once on the compute streams.  d_tickets[1 + w] (zeroed above) is that launch's block ticket.
+        cudaStream_t cs = d.cstreams[w % d.cstreams.size()];
+        if (!check(cudaEventRecord(d.window_events[w], st))) break;
+        if (!check(cudaStreamWaitEvent(cs, d.window_events[w], 0))) break;
+        InflateArgs a{};
+        a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart; a.scratch = d.d_t1_scratch;
+        a.b0 = win.b0; a.b1 = win.b1; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets + 1 + w; a.fail_count = d.d_cnt + 0;
+        const uint32_t nbw = win.b1 - win.b0;
+        kd_inflate_t1<<<(nbw + T1_THREADS - 1) / T1_THREADS, T1_THREADS, T1_SMEM_BYTES, cs>>>(a);
+        kd_crc32<<<std::max<uint32_t>(1, (nbw + 7) / 8), 256, 0, cs>>>(a);
+        if (!check(cudaGetLastError())) break;
+      } else if (!check(cudaMemcpyAsync(d.d_tickets + 1 + w, d.h_ones, 4, cudaMemcpyHostToDevice, st))) {  // window w has arrived
+        break;
+      }
     }
     check(cudaEventRecord(d.done_events[t], st));
   };
@@ -1220,6 +1300,12 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
   out->h2d_bytes = (byte_hi - byte_lo) + 24ull * nb + 8;
   if (first_err.load()) return fail(c, CMB_E_CUDA, "cmb_submit_bgzf: copy/inflate stage failed: %s", cudaGetErrorString((cudaError_t)first_err.load()));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(c->stream, d.done_events[t], 0));
+  if (per_window) {
+    for (size_t k = 0; k < std::min<size_t>(NCS, windows.size()); ++k) {
+      CU_TRY(c, cudaEventRecord(d.cstream_done[k], d.cstreams[k]));
+      CU_TRY(c, cudaStreamWaitEvent(c->stream, d.cstream_done[k], 0));
+    }
+  }
   CU_TRY(c, cudaEventRecord(d.ev[2], c->stream));
   if (getenv("CMB_DECODE_PROFILE")) {  // debugging aid: the inflate kernel alone, all blocks resident, one launch
     CU_TRY(c, cudaStreamSynchronize(c->stream));
@@ -1228,7 +1314,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     cudaEventCreate(&p1);
     CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4, c->stream));
     InflateArgs a{};
-    a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart;
+    a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart; a.scratch = d.d_t1_scratch;
     a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 8;
     cudaEventRecord(p0, c->stream);
     if ((rc = launch_inflate(c, a, c->stream))) return rc;
@@ -1270,7 +1356,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
         CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4, c->stream));
         CU_TRY(c, cudaMemsetAsync(d.d_cnt, 0, 4, c->stream));
         InflateArgs a2{};
-        a2.comp = comp_base; a2.coff = d.d_coff; a2.clen = d.d_clen; a2.isize = d.d_isize; a2.uoff = d.d_ustart;
+        a2.comp = comp_base; a2.coff = d.d_coff; a2.clen = d.d_clen; a2.isize = d.d_isize; a2.uoff = d.d_ustart; a2.scratch = d.d_t1_scratch;
         a2.b0 = 0; a2.b1 = (uint32_t)again.size(); a2.out = infl_base; a2.status = d.d_status; a2.ticket = d.d_tickets;
         a2.fail_count = d.d_cnt + 0; a2.block_list = d_list;
         if ((rc = launch_inflate(c, a2, c->stream, false))) return rc;
@@ -1417,6 +1503,43 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     memcpy(&out->n_primary, h_cnt + 4, 8);
     memcpy(&out->n_records, h_cnt + 10, 8);  // records this call owns (all of them unless ranged)
     d.last_valid = true;
+    d.last_mate = nullptr;
+    if (c->mode.filter_pairs) {  // mate matching on the device (filter.rs:117-233; cmb_pairs.cuh)
+      if (d.pair_rec_cap < (size_t)n_rec || !d.d_pair_key) {
+        cudaFree(d.d_pair_key); cudaFree(d.d_pair_mate); cudaFree(d.d_pair_next);
+        d.d_pair_key = nullptr; d.d_pair_mate = nullptr; d.d_pair_next = nullptr; d.pair_rec_cap = 0;
+        const size_t want = (size_t)n_rec + (size_t)n_rec / 8 + 16;
+        CU_TRY(c, cudaMalloc(&d.d_pair_key, 8 * want));
+        CU_TRY(c, cudaMalloc(&d.d_pair_mate, 4 * want));
+        CU_TRY(c, cudaMalloc(&d.d_pair_next, 4 * want));
+        d.pair_rec_cap = want;
+      }
+      size_t table = 1u << 16;
+      while (table < 2 * (size_t)n_rec) table <<= 1;
+      if (d.pair_table_cap < table) {
+        cudaFree(d.d_pair_tag); cudaFree(d.d_pair_head);
+        d.d_pair_tag = nullptr; d.d_pair_head = nullptr; d.pair_table_cap = 0;
+        CU_TRY(c, cudaMalloc(&d.d_pair_tag, 8 * table));
+        CU_TRY(c, cudaMalloc(&d.d_pair_head, 4 * table));
+        d.pair_table_cap = table;
+      }
+      CU_TRY(c, cudaMemsetAsync(d.d_pair_tag, 0, 8 * table, c->stream));
+      CU_TRY(c, cudaMemsetAsync(d.d_pair_head, 0xff, 4 * table, c->stream));
+      PairArgs pa{};
+      pa.data = infl_base; pa.rec_off = d.d_rec_off; pa.n_records = (uint32_t)n_rec; pa.key = d.d_pair_key; pa.mate = d.d_pair_mate;
+      pa.next = d.d_pair_next; pa.slot_tag = d.d_pair_tag; pa.slot_head = d.d_pair_head; pa.table_mask = (uint32_t)(table - 1);
+      pa.flags = d.d_cnt + 1;
+      const uint32_t gr = (uint32_t)((n_rec + 255) / 256);
+      kd_pair_keys<<<gr, 256, 0, c->stream>>>(pa);
+      kd_pair_insert<<<gr, 256, 0, c->stream>>>(pa);
+      kd_pair_resolve<<<(uint32_t)((table + 255) / 256), 256, 0, c->stream>>>(pa);
+      CU_TRY(c, cudaGetLastError());
+      out->n_launches += 3;
+      CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
+      CU_TRY(c, cudaStreamSynchronize(c->stream));
+      if (h_cnt[1]) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: mate matching gave up (flags %u)", h_cnt[1]);
+      d.last_mate = d.d_pair_mate;
+    }
     CU_TRY(c, cudaEventRecord(d.ev[4], c->stream));
     if (c->n_local) {
       // records that start before excl_end_block are this rank's exclusive share of the stream (cmb_kept_tid_range)
@@ -1430,7 +1553,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
           excl_n = (uint32_t)base;
         }
       }
-      rc = launch_k1(c, tb, (uint32_t)n_rec, (uint32_t)n_cig, excl_n);
+      rc = launch_k1(c, tb, (uint32_t)n_rec, (uint32_t)n_cig, excl_n, d.last_mate);
       if (rc) return rc;
     }
   } else {

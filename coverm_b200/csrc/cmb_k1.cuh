@@ -27,10 +27,13 @@ struct K1Args {
   cmb_contig_stats* rows;
   int2* block_minmax;  // per block {min kept tid, max kept tid} for the cross-block sortedness check
   uint32_t* error_flags;
-  // cross-RANK half of the sortedness check (multi-GPU): kept tid range of the records with index < excl_n, as
-  // kept_range[0] = max(tid + 1), kept_range[1] = max(INT_MAX - tid)  (0 = none yet)
-  uint32_t* kept_range;
+  // cross-RANK half of the sortedness check (multi-GPU contig sharding only, else NULL): per block {min, max} kept tid of
+  // the records with index < excl_n (INT_MAX / INT_MIN = none); k1c_check_sorted folds them into the rank's kept range
+  int2* block_xrange;
   uint32_t excl_n;
+  // pair path: partner of each record (cmb_pairs.cuh, records in file order) or NULL = the host layout (completed pairs
+  // only, stored first mate at the even index, its partner right after)
+  const int32_t* mate;
   // params
   cmb_params p;
   uint8_t filter_single, filter_pairs;
@@ -96,9 +99,11 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
       const bool passes_filter1 = !unmapped && (p.include_supplementary || !supplementary) && (p.include_secondary || !secondary);
       passes = passes_filter1 && single_read_passes(r, p, &nm_err);
     } else {  // filter.rs:117-233: the host submits completed pairs only; stored first mate at the even index
-      const uint32_t m = i ^ 1u;
+      const int32_t mi = a.mate ? a.mate[i] : (int32_t)(i ^ 1u);
+      const uint32_t m = (uint32_t)mi;
       RecView o = {};
-      const bool have_mate = m < a.n;
+      const bool have_mate = mi >= 0 && m < a.n;
+      const bool i_is_second = a.mate ? m < i : (i & 1u);  // the stored first mate is the earlier record
       if (have_mate) {
         o.flag = a.flag[m];
         o.mapq = a.mapq[m];
@@ -108,8 +113,8 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
         o.aligned = a.aligned[m];
         o.del = a.del[m];
       }
-      const RecView& first = (i & 1u) ? o : r;   // record1 (stored)
-      const RecView& second = (i & 1u) ? r : o;  // record (just read)
+      const RecView& first = i_is_second ? o : r;   // record1 (stored)
+      const RecView& second = i_is_second ? r : o;  // record (just read)
       bool ok = have_mate;
       if (ok && a.filter_single) ok = single_read_passes(first, p, &nm_err) && single_read_passes(second, p, &nm_err);
       if (ok) ok = read_pair_passes(second, first, p, &nm_err);
@@ -143,16 +148,26 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
     for (int d = 16; d > 0; d >>= 1) kmin = min(kmin, __shfl_xor_sync(FULL, kmin, d));
     if (lane == 31) s_wmax[warp] = pm;
     if (lane == 0) s_wmin[warp] = kmin;
-    {
+    __shared__ int s_xmax[K1_THREADS / 32];
+    __shared__ int s_xmin[K1_THREADS / 32];
+    if (a.block_xrange) {
       const bool xk = keep && i < a.excl_n;
-      const uint32_t xmax = __reduce_max_sync(FULL, xk ? (uint32_t)tid + 1u : 0u);
-      const uint32_t xmin = __reduce_max_sync(FULL, xk ? (uint32_t)(INT_MAX - tid) : 0u);
-      if (lane == 0 && xmax) {
-        atomicMax(a.kept_range + 0, xmax);
-        atomicMax(a.kept_range + 1, xmin);
+      const int xmax = __reduce_max_sync(FULL, xk ? tid : INT_MIN);
+      const int xmin = __reduce_min_sync(FULL, xk ? tid : INT_MAX);
+      if (lane == 0) {
+        s_xmax[warp] = xmax;
+        s_xmin[warp] = xmin;
       }
     }
     __syncthreads();
+    if (a.block_xrange && threadIdx.x == 0) {
+      int xmax = INT_MIN, xmin = INT_MAX;
+      for (uint32_t w = 0; w < K1_THREADS / 32; ++w) {
+        xmax = max(xmax, s_xmax[w]);
+        xmin = min(xmin, s_xmin[w]);
+      }
+      a.block_xrange[blockIdx.x] = make_int2(xmin, xmax);
+    }
     int before = INT_MIN;
     for (uint32_t w = 0; w < warp; ++w) before = max(before, s_wmax[w]);
     if (keep && tid < max(before, excl)) err |= ERR_UNSORTED;
@@ -251,11 +266,28 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
 }
 
 // Cross-block sortedness: block b's smallest kept tid must be >= every earlier block's largest.
-__global__ void __launch_bounds__(1024) k1c_check_sorted(const int2* block_minmax, uint32_t n_blocks, uint32_t* error_flags) {
+// With block_xrange (multi-GPU): also folds the blocks' exclusive kept tid ranges into kept_range[0] = max tid + 1 (0 = none),
+// kept_range[1] = INT_MAX - min tid.
+__global__ void __launch_bounds__(1024) k1c_check_sorted(const int2* block_minmax, uint32_t n_blocks, uint32_t* error_flags,
+                                                         const int2* block_xrange, uint32_t* kept_range) {
   __shared__ int s_max[1024];
   const uint32_t t = threadIdx.x;
   const uint32_t per = (n_blocks + 1023) / 1024;
   const uint32_t b0 = t * per, b1 = min(n_blocks, b0 + per);
+  if (block_xrange) {
+    int xmin = INT_MAX, xmax = INT_MIN;
+    for (uint32_t b = b0; b < b1; ++b) {
+      const int2 x = block_xrange[b];
+      xmin = min(xmin, x.x);
+      xmax = max(xmax, x.y);
+    }
+    xmin = __reduce_min_sync(FULL, xmin);
+    xmax = __reduce_max_sync(FULL, xmax);
+    if ((t & 31) == 0 && xmax != INT_MIN) {
+      atomicMax(kept_range + 0, (uint32_t)xmax + 1u);
+      atomicMax(kept_range + 1, (uint32_t)(INT_MAX - xmin));
+    }
+  }
   int lmax = INT_MIN;
   bool bad = false;
   for (uint32_t b = b0; b < b1; ++b) {

@@ -124,19 +124,17 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
     const uint8_t* rowp = smem + s * CHUNK_BYTES + row * 128;
     const uint32_t span = chunk * CHUNK_SPANS + t;
     int total = 0;
-    uint32_t ev = 0;  // bit j: the 16-byte unit j (4 positions) of the span holds a non-zero delta
+    uint32_t ev = 0;
     {
       int4* g = reinterpret_cast<int4*>(a.arena + (uint64_t)span * SPAN);
 #pragma unroll
       for (uint32_t j = 0; j < UNITS; ++j) {
         const uint32_t unit = (u0 + j) ^ (row & 7);
         const int4 q = *reinterpret_cast<const int4*>(rowp + unit * 16);
-        // one OR tree per unit instead of one compare per position: deltas are sparse (~1 % of the positions), the
-        // positions inside a marked unit are told apart in the run loop below
-        const bool any = ((q.x | q.y) | (q.z | q.w)) != 0;
+        const uint32_t e4 = (q.x != 0 ? 1u : 0u) | (q.y != 0 ? 2u : 0u) | (q.z != 0 ? 4u : 0u) | (q.w != 0 ? 8u : 0u);
         total += (q.x + q.y) + (q.z + q.w);
-        if (any) ev |= 1u << j;
-        if (CLEAN && any) g[j] = make_int4(0, 0, 0, 0);  // re-zero only the 16 B units that hold an event
+        ev |= e4 << (4 * j);
+        if (CLEAN && e4) g[j] = make_int4(0, 0, 0, 0);  // re-zero only the 16 B units that hold an event
       }
     }
 
@@ -267,20 +265,12 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
       uint32_t from = 0;
       uint32_t m = ev;
       while (m) {
-        const uint32_t ju = (uint32_t)__ffs(m) - 1;
+        const uint32_t j = (uint32_t)__ffs(m) - 1;
         m &= m - 1;
-        const uint32_t unit = (u0 + ju) ^ (row & 7);
-        const int4 q = *reinterpret_cast<const int4*>(rowp + unit * 16);  // the tile stays resident until the next barrier
-        const int dl[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-        for (uint32_t k = 0; k < 4; ++k) {
-          if (dl[k] != 0) {
-            const uint32_t j = ju * 4 + k;
-            close_run(depth, from, j);
-            depth += dl[k];
-            from = j;
-          }
-        }
+        close_run(depth, from, j);
+        const uint32_t unit = (u0 + (j >> 2)) ^ (row & 7);
+        depth += *reinterpret_cast<const int*>(rowp + unit * 16 + (j & 3) * 4);  // the delta at position j
+        from = j;
       }
       close_run(depth, from, SPAN);
     } else {  // no event in the span: constant depth

@@ -183,6 +183,7 @@ class InflateStream {
     if (bad) throw Panic("Error reading BAM record: BGZF inflate failed");
     return true;
   }
+  void set_window(size_t window_bytes) { window_ = window_bytes; }
   uint64_t compressed_bytes() const { return n_; }
   // uncompressed / fully inflated inputs: the raw byte range (BlockIndex cuts it into slices)
   bool is_raw() const { return kind_ == RAW; }

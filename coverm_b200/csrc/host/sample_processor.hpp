@@ -403,8 +403,8 @@ class DeviceSession {
     rc = cmb_set_params(ctx_, &params, &mode);
     if (rc) throw_device_error(ctx_, rc);
     const bool pair_mode = mode.filter_pairs;
-    // pair mode decodes window by window (mate matching is sequential); otherwise only the header is read here
-    InflateStream stream(p, n, pool_, pair_mode ? (48u << 20) : (1u << 20));
+    // only the header is read through this stream, unless the host's mate-matching fallback below needs the records too
+    InflateStream stream(p, n, pool_, 1u << 20);
     std::vector<uint8_t> buf;
     size_t begin = 0;  // first unconsumed byte of buf
     auto need = [&](size_t bytes_needed) {  // make buf[begin, begin+bytes_needed) available; false at EOF
@@ -518,14 +518,16 @@ class DeviceSession {
       }
     };
 
-    if (!pair_mode) {
+    bool decoded_on_device = false;
+    {
       // region-parallel pipeline (decode_runner.hpp): this thread only acquires / submits staging batches
       BlockIndex bx;
       if (stream.is_raw()) bx.build(stream.raw_data(), stream.raw_size());
       else bx.build(p, n);
       // Device-side decode first (compressed blocks cross PCIe, the GPU inflates and parses them); the host pipeline
-      // below runs when the input is not BGZF, when CMB_HOST_DECODE is set, or when the device declines the stream.
-      bool decoded_on_device = false;
+      // below runs when the input is not BGZF, when CMB_HOST_DECODE is set, or when the device declines the stream.  Pair
+      // filtering included: the device matches mates itself (cmb_pairs.cuh); the host's BTreeMap-style matching further
+      // down is the fallback.
       if (bx.bgzf && !stream.is_raw() && !getenv("CMB_HOST_DECODE")) {
         const size_t nb = bx.blocks.size();
         std::vector<uint64_t> coff(nb);
@@ -586,7 +588,7 @@ class DeviceSession {
           fprintf(stderr, "#device_decode\tdeclined: %s\n", cmb_last_error(ctx_));
         }
       }
-      if (!decoded_on_device) {
+      if (!decoded_on_device && !pair_mode) {
       if (shard) shard->counts_global = true;  // every rank's host decoder reads the whole file; K1 keeps the rank's own tids
       const PipelineCounts pc = run_decode_pipeline(
           bx, records_at, n_ref, pool_.size(), batch_records_, batch_intervals_, n_staging_, scratch_,
@@ -608,7 +610,9 @@ class DeviceSession {
         fprintf(stderr, "#pipeline\titems=%u\tworkers=%u\tinflate_s=%.3f\tchain_s=%.3f\textract_s=%.3f\tidle_s=%.3f (summed over workers)\n",
                 pc.n_items, pc.n_workers, pc.inflate_s, pc.scan_s, pc.extract_s, pc.idle_s);
       }
-    } else for (;;) {
+    }
+    if (pair_mode && !decoded_on_device) stream.set_window(48u << 20);  // mate matching is sequential: decode window by window
+    if (pair_mode && !decoded_on_device) for (;;) {
       if (shard) shard->counts_global = true;  // mate matching reads the whole file on every rank
       // complete records currently in buf
       rec_off.clear();

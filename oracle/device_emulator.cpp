@@ -220,7 +220,6 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
     c->err = "device emulator: no device-side decode";
     return CMB_E_DECLINED;
   }
-  if (c->mode.filter_pairs) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: pair filtering needs host mate matching");
   *out = cmb_bgzf_result{};
   // like the device: only the blocks of the range (plus a tail for its last straddling record) are inflated; `stream`
   // is indexed with absolute uncompressed offsets through `base`
@@ -262,6 +261,8 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
   std::vector<uint16_t> flag;
   std::vector<uint8_t> mapq, nm_state;
   std::vector<uint32_t> nm, l_seq, aligned, del, ins, iv_begin;
+  std::vector<int32_t> mtid;
+  std::vector<std::string> qname;
   size_t o = in->records_at - base;
   const size_t walk_stop = (size_t)(ustart[walk_end] - base);  // records starting at or after this belong to the next range
   size_t excl_n = (size_t)-1;
@@ -278,6 +279,8 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
     mapq.push_back(stream[r + 9]);
     flag.push_back((uint16_t)u16(r + 14));
     l_seq.push_back(ls);
+    mtid.push_back((int32_t)u32(r + 20));
+    qname.emplace_back((const char*)stream.data() + r + 32, l_name ? l_name - 1 : 0);
     const bool owned = !in->ranged || (tid.back() < 0 ? in->own_unplaced != 0 : (tid.back() >= in->own_tid_begin && tid.back() < in->own_tid_end));
     n_owned += owned;
     if (owned && !(flag.back() & 0x900)) out->n_primary += 1;
@@ -336,6 +339,55 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
   out->h2d_bytes = in->size;
   if (tid.empty()) return CMB_OK;
   if (ivs.empty()) { ivs.push_back(0); ivl.push_back(0); }
+  if (c->mode.filter_pairs) {
+    // the pair path of ReferenceSortedBamFilter::read (filter.rs:117-233) as the reference runs it -- a map of stored first
+    // mates, cleared when the reference id changes -- then only completed pairs, stored mate first, in the host layout
+    // K1's emulation expects (first at the even index).  The CUDA library matches mates with a hash table instead
+    // (cmb_pairs.cuh) and leaves the records in file order; both must give the oracle's table.
+    std::map<std::string, size_t> first_set;
+    int32_t current = -1;
+    std::vector<size_t> order;
+    for (size_t i = 0; i < tid.size(); ++i) {
+      if ((flag[i] & 0x900) || !(flag[i] & 0x2)) continue;
+      if (tid[i] != current) {
+        current = tid[i];
+        first_set.clear();
+      }
+      auto it = first_set.find(qname[i]);
+      if (it == first_set.end()) {
+        if (mtid[i] == current) first_set.emplace(qname[i], i);
+      } else {
+        order.push_back(it->second);
+        order.push_back(i);
+        first_set.erase(it);
+      }
+    }
+    auto pick = [&](auto& v) {
+      auto w = v;
+      w.clear();
+      for (size_t i : order) w.push_back(v[i]);
+      v.swap(w);
+    };
+    std::vector<int32_t> ivs2, ivl2;
+    std::vector<uint32_t> ivb2;
+    for (size_t i : order) {
+      ivb2.push_back((uint32_t)ivs2.size());
+      for (uint32_t k = iv_begin[i]; k < iv_begin[i + 1]; ++k) {
+        ivs2.push_back(ivs[k]);
+        ivl2.push_back(ivl[k]);
+      }
+    }
+    ivb2.push_back((uint32_t)ivs2.size());
+    pick(tid); pick(pos); pick(flag); pick(mapq); pick(nm_state); pick(nm); pick(l_seq); pick(aligned); pick(del); pick(ins);
+    ivs.swap(ivs2); ivl.swap(ivl2); iv_begin.swap(ivb2);
+    if (excl_n != (size_t)-1) {  // pairs are ordered by their second mate: those completed inside the exclusive share form a prefix
+      size_t k = 0;
+      while (k + 1 < order.size() && order[k + 1] < excl_n) k += 2;
+      excl_n = k;
+    }
+    if (tid.empty()) return CMB_OK;
+    if (ivs.empty()) { ivs.push_back(0); ivl.push_back(0); }
+  }
   cmb_read_batch b{};
   b.tid = tid.data(); b.pos = pos.data(); b.flag = flag.data(); b.mapq = mapq.data(); b.nm_state = nm_state.data(); b.nm = nm.data();
   b.l_seq = l_seq.data(); b.aligned = aligned.data(); b.del = del.data(); b.ins = ins.data(); b.iv_begin = iv_begin.data();

@@ -35,7 +35,7 @@ static const uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4
 struct InflateArgs {
   const uint8_t* comp; const uint64_t* coff; const uint32_t* clen; const uint32_t* isize; const uint64_t* uoff;
   uint32_t b0, b1; uint8_t* out; uint32_t* status; uint32_t* ticket; uint32_t* fail_count;
-  const uint32_t* block_window; const uint32_t* ready; const uint32_t* block_list;
+  const uint32_t* block_window; const uint32_t* ready; const uint32_t* block_list; uint8_t* scratch;
 };
 uint8_t t1_smem[4096];
 #include "cmb_decode_t1.cuh"
@@ -74,6 +74,8 @@ static void run(const vector<vector<uint8_t>>& comp, const vector<uint32_t>& isi
   InflateArgs a{};
   a.comp = file.data(); a.coff = coff.data(); a.clen = clen.data(); a.isize = isize.data(); a.uoff = uoff.data();
   a.b0 = 0; a.b1 = (uint32_t)comp.size(); a.out = inflated.data(); a.status = status.data(); a.ticket = &ticket; a.fail_count = &fails;
+  vector<uint8_t> scratch(comp.size() * 160 + 16, 0x77);
+  a.scratch = scratch.data();
   kd_inflate_t1(a);
   out.clear();
   for (size_t i = 0; i < comp.size(); ++i) {

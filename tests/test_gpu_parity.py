@@ -206,3 +206,44 @@ def test_in_memory_bam_through_the_c_abi(synth):
 def test_smoke_entry():
     import __graft_entry__
     __graft_entry__.smoke()
+
+
+# ---------------------------------------------------------------------------------------------- pair path on the device
+PAIR_RUNS = [
+    ("small", ["contig", "-m", "mean", "variance", "count", "--proper-pairs-only", "--min-read-aligned-length-pair", "250", "--min-read-percent-identity-pair", "95"]),
+    ("small", ["contig", "-m", "mean", "count", "--proper-pairs-only", "--min-mapq", "30", "--min-read-aligned-percent", "95"]),
+    ("small", ["contig", "-m", "mean", "trimmed_mean", "--proper-pairs-only", "--min-read-aligned-percent-pair", "0.9", "--min-read-aligned-length", "100"]),
+    ("mags", ["genome", "-s", "~", "-m", "mean", "covered_fraction", "--proper-pairs-only", "--min-read-percent-identity-pair", "97", "--min-covered-fraction", "0"]),
+    ("deep", ["contig", "-m", "mean", "variance", "--proper-pairs-only", "--min-read-aligned-length-pair", "280"]),
+]
+
+
+@pytest.mark.parametrize("which,argv", PAIR_RUNS, ids=[f"{w}:{' '.join(a[3:8])}#{i}" for i, (w, a) in enumerate(PAIR_RUNS)])
+def test_pair_filter_stays_on_the_device(synth, which, argv):
+    """Mate matching of ReferenceSortedBamFilter's pair path (filter.rs:117-233) runs on the GPU (cmb_pairs.cuh): the sample is
+    decoded by cmb_submit_bgzf, not by the host pipeline, and the table equals the oracle's; the host's own mate matching
+    (CMB_HOST_DECODE=1) must agree too."""
+    g = _assert_same(argv + ["-b", synth[which]], env={"CMB_PIPELINE_STATS": "1"})
+    assert any(l.startswith("#device_decode\tblocks=") for l in g.stderr.splitlines()), g.stderr[-800:]
+    _assert_same(argv + ["-b", synth[which]], env={"CMB_HOST_DECODE": "1"})
+
+
+FILTER_RS_PAIR_SETTINGS = [  # (fixture, --min-read-aligned-length-pair, --min-read-percent-identity-pair, --min-read-aligned-percent-pair): filter.rs:342-599
+    ("7seqs.reads_for_seq1_and_seq2.bam", 90, 0.99, 0.0), ("2seqs.bad_read.1.bam", 250, 0.99, 0.0), ("2seqs.bad_read.1.bam", 300, 0.98, 0.0),
+    ("2seqs.bad_read.1.with_extra.bam", 0, 0.98, 0.94), ("2seqs.bad_read.1.bam", 299, 0.98, 0.0), ("eg2.bam", 1, 0.0, 0.0), ("1.bam", 120, 0.95, 0.9),
+]
+
+
+@pytest.mark.parametrize("bam,length,identity,percent", FILTER_RS_PAIR_SETTINGS, ids=[f"{b}:{l}:{i}:{p}" for b, l, i, p in FILTER_RS_PAIR_SETTINGS])
+def test_pair_filter_settings_of_the_reference_tests_on_the_device(bam, length, identity, percent):
+    """The fixtures and thresholds of the reference's pair-filter unit tests (filter.rs:342-599; the oracle reproduces their
+    qname sequences, tests/test_oracle_golden.py) through the device's mate matching: read counts and coverage as the oracle."""
+    argv = ["contig", "-m", "mean", "count", "covered_bases", "--proper-pairs-only", "--min-covered-fraction", "0"]
+    if length:
+        argv += ["--min-read-aligned-length-pair", str(length)]
+    if identity:
+        argv += ["--min-read-percent-identity-pair", str(identity)]
+    if percent:
+        argv += ["--min-read-aligned-percent-pair", str(percent)]
+    g = _assert_same(argv + ["-b", os.path.join(DATA, bam)], env={"CMB_PIPELINE_STATS": "1"})
+    assert any(l.startswith("#device_decode\tblocks=") for l in g.stderr.splitlines()), g.stderr[-800:]
