@@ -147,6 +147,11 @@ struct cmb_ctx {
   int2* d_block_xrange = nullptr;  // same capacity as d_block_minmax
   bool have_xrange = false;
   uint32_t block_minmax_capacity = 0, block_minmax_used = 0;
+  // gene mode (cmb_set_genes): segments are genes; records carry contig tids
+  bool gene_mode = false;
+  uint32_t n_ref_contigs = 0;  // contigs of the BAM header (== n_contigs outside gene mode)
+  uint32_t *d_gene_first = nullptr, *d_gene_start = nullptr, *d_gene_end = nullptr, *d_gene_maxlen = nullptr, *d_contig_len32 = nullptr;
+  uint8_t* d_contig_seen = nullptr;
   CUtensorMap tmap{};
   bool arena_dirty = true;
   bool clean_as_you_go = true;
@@ -283,6 +288,11 @@ void free_reference(cmb_ctx* c) {
   cudaFree(c->d_ovf_head);
   c->d_ovf_head = nullptr;
   cudaFree(c->d_pairs);
+  cudaFree(c->d_gene_first); cudaFree(c->d_gene_start); cudaFree(c->d_gene_end); cudaFree(c->d_gene_maxlen); cudaFree(c->d_contig_len32);
+  cudaFree(c->d_contig_seen);
+  c->d_gene_first = c->d_gene_start = c->d_gene_end = c->d_gene_maxlen = c->d_contig_len32 = nullptr;
+  c->d_contig_seen = nullptr;
+  c->gene_mode = false;
   c->d_arena = nullptr;
   c->d_off_span = c->d_len = c->d_chunk_first = nullptr;
   c->d_tail_sum = c->d_carry_in = nullptr;
@@ -321,7 +331,11 @@ int launch_k1(cmb_ctx* c, const cmb_read_batch& b, uint32_t n_records, uint32_t 
   a.iv_start = b.iv_start; a.iv_len = b.iv_len;
   a.n = n_records;
   a.off_span = c->d_off_span; a.len = c->d_len;
-  a.n_contigs = c->n_contigs; a.tid_begin = c->tid_begin; a.tid_end = c->tid_end;
+  a.n_contigs = c->gene_mode ? c->n_ref_contigs : c->n_contigs; a.tid_begin = c->tid_begin; a.tid_end = c->tid_end;
+  if (c->gene_mode) {
+    a.gene_first = c->d_gene_first; a.gene_start = c->d_gene_start; a.gene_end = c->d_gene_end; a.gene_maxlen = c->d_gene_maxlen;
+    a.contig_len = c->d_contig_len32; a.contig_seen = c->d_contig_seen; a.kept_primary = (unsigned long long*)(c->d_counters + 8);
+  }
   a.arena = c->d_arena; a.tail_sum = c->d_tail_sum; a.rows = c->d_rows;
   a.block_minmax = c->d_block_minmax + c->block_minmax_used;
   a.error_flags = c->d_counters + 0;
@@ -405,7 +419,7 @@ int run_end_of_sample(cmb_ctx* c) {
     k.rec = c->d_rec; k.warp_table = c->d_warp_table; k.ovf = c->d_ovf; k.ovf_head = c->d_ovf_head;
     k.ovf_capacity = c->ovf_capacity;
     k.pairs = c->d_pairs; k.pair_count = (unsigned long long*)(c->d_counters + 4); k.pair_capacity = c->pair_capacity;
-    k.want_csr = csr; k.error_flags = c->d_counters + 0;
+    k.want_csr = csr; k.all_rows = c->gene_mode ? 1u : 0u; k.error_flags = c->d_counters + 0;
     const uint32_t grid = (c->n_local + K3_WARPS - 1) / K3_WARPS;  // one warp per contig
     k3_finalize<<<grid, K3_THREADS, 0, c->stream>>>(k);
     CU_TRY(c, cudaGetLastError());
@@ -566,12 +580,68 @@ void cmb_destroy(cmb_ctx* c) {
   delete c;
 }
 
+int cmb_set_genes(cmb_ctx* c, uint32_t n_contigs, const uint64_t* contig_len, uint32_t n_genes, const cmb_gene* genes) {
+  if (!c || (!contig_len && n_contigs) || (!genes && n_genes)) return fail(c, CMB_E_ARG, "cmb_set_genes: null argument");
+  if (c->in_sample) return fail(c, CMB_E_ARG, "cmb_set_genes: a sample is in progress");
+  std::vector<uint64_t> seg_len(std::max<uint32_t>(1, n_genes), 1);
+  std::vector<uint32_t> first((size_t)n_contigs + 1, 0), gs(std::max<uint32_t>(1, n_genes)), ge(std::max<uint32_t>(1, n_genes)), maxlen(std::max<uint32_t>(1, n_contigs), 0), clen(std::max<uint32_t>(1, n_contigs), 0);
+  for (uint32_t t = 0; t < n_contigs; ++t) {
+    if (contig_len[t] > 0x7fffffffull) return fail(c, CMB_E_ARG, "cmb_set_genes: contig %u longer than 2^31-1", t);
+    clen[t] = (uint32_t)contig_len[t];
+  }
+  for (uint32_t g = 0; g < n_genes; ++g) {
+    const cmb_gene& x = genes[g];
+    if (x.tid >= n_contigs || x.start >= x.end || x.end > contig_len[x.tid]) return fail(c, CMB_E_ARG, "cmb_set_genes: gene %u is not a range of its contig", g);
+    if (g && (genes[g - 1].tid > x.tid || (genes[g - 1].tid == x.tid && genes[g - 1].start > x.start)))
+      return fail(c, CMB_E_ARG, "cmb_set_genes: genes must be sorted by (tid, start)");
+    seg_len[g] = x.end - x.start;
+    gs[g] = x.start;
+    ge[g] = x.end;
+    first[x.tid + 1] += 1;
+    maxlen[x.tid] = std::max(maxlen[x.tid], x.end - x.start);
+  }
+  for (uint32_t t = 0; t < n_contigs; ++t) first[t + 1] += first[t];
+  // the arena, rows and histogram buffers are laid out over the genes exactly as over contigs (a placeholder segment keeps an
+  // empty gene set well-formed)
+  const uint32_t n_seg = std::max<uint32_t>(1, n_genes);
+  int rc = cmb_set_reference(c, n_seg, seg_len.data(), 0, n_seg);
+  if (rc) return rc;
+  c->gene_mode = true;
+  c->n_ref_contigs = n_contigs;
+  CU_TRY(c, cudaMalloc(&c->d_gene_first, 4ull * (n_contigs + 1)));
+  CU_TRY(c, cudaMalloc(&c->d_gene_start, 4ull * n_seg));
+  CU_TRY(c, cudaMalloc(&c->d_gene_end, 4ull * n_seg));
+  CU_TRY(c, cudaMalloc(&c->d_gene_maxlen, 4ull * std::max<uint32_t>(1, n_contigs)));
+  CU_TRY(c, cudaMalloc(&c->d_contig_len32, 4ull * std::max<uint32_t>(1, n_contigs)));
+  CU_TRY(c, cudaMalloc(&c->d_contig_seen, std::max<size_t>(1, n_contigs)));
+  CU_TRY(c, cudaMemcpyAsync(c->d_gene_first, first.data(), 4ull * (n_contigs + 1), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_gene_start, gs.data(), 4ull * n_seg, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_gene_end, ge.data(), 4ull * n_seg, cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_gene_maxlen, maxlen.data(), 4ull * std::max<uint32_t>(1, n_contigs), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(c->d_contig_len32, clen.data(), 4ull * std::max<uint32_t>(1, n_contigs), cudaMemcpyHostToDevice, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return CMB_OK;
+}
+
+int cmb_fetch_gene_extras(cmb_ctx* c, uint8_t* contig_seen, uint64_t* n_kept_primary) {
+  if (!c || !contig_seen || !n_kept_primary) return fail(c, CMB_E_ARG, "cmb_fetch_gene_extras: null argument");
+  if (!c->gene_mode || !c->ended) return fail(c, CMB_E_ARG, "cmb_fetch_gene_extras: no ended sample in gene mode");
+  CU_TRY(c, cudaSetDevice(c->device));
+  unsigned long long kp = 0;
+  if (c->n_ref_contigs) CU_TRY(c, cudaMemcpyAsync(contig_seen, c->d_contig_seen, c->n_ref_contigs, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(&kp, c->d_counters + 8, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  *n_kept_primary = kp;
+  return CMB_OK;
+}
+
 int cmb_set_reference(cmb_ctx* c, uint32_t n_contigs, const uint64_t* contig_len, uint32_t tid_begin, uint32_t tid_end) {
   if (!c || !contig_len || tid_begin > tid_end || tid_end > n_contigs) return fail(c, CMB_E_ARG, "cmb_set_reference: bad arguments");
   if (c->in_sample) return fail(c, CMB_E_ARG, "cmb_set_reference: a sample is in progress");
   CU_TRY(c, cudaSetDevice(c->device));
   free_reference(c);
   c->n_contigs = n_contigs;
+  c->n_ref_contigs = n_contigs;
   c->tid_begin = tid_begin;
   c->tid_end = tid_end;
   c->n_local = tid_end - tid_begin;
@@ -671,6 +741,7 @@ int cmb_begin_sample(cmb_ctx* c) {
   }
   CU_TRY(c, cudaMemsetAsync(c->d_rows, 0, sizeof(cmb_contig_stats) * (size_t)c->n_contigs, c->stream));
   CU_TRY(c, cudaMemsetAsync(c->d_counters, 0, 64, c->stream));
+  if (c->gene_mode) CU_TRY(c, cudaMemsetAsync(c->d_contig_seen, 0, std::max<size_t>(1, c->n_ref_contigs), c->stream));
   CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
   c->arena_dirty = true;  // until K2 has cleaned it
   if ((c->params.want & CMB_WANT_HIST_CSR) && c->n_local) {

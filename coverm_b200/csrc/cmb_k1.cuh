@@ -31,6 +31,14 @@ struct K1Args {
   // the records with index < excl_n (INT_MAX / INT_MIN = none); k1c_check_sorted folds them into the rank's kept range
   int2* block_xrange;
   uint32_t excl_n;
+  // per-gene coverage (genes.rs): the arena's segments are genes, records carry contig tids.  NULL = contig mode.
+  const uint32_t* gene_first;   // [n_contigs + 1] first gene of each contig (genes sorted by (tid, start))
+  const uint32_t* gene_start;   // [n_genes] gene range on its contig, clamped to the contig
+  const uint32_t* gene_end;
+  const uint32_t* gene_maxlen;  // [n_contigs] longest gene of the contig (bounds the backward search for overlaps)
+  const uint32_t* contig_len;   // [n_contigs]
+  uint8_t* contig_seen;         // [n_contigs] a kept record mapped here (genes.rs:220-246)
+  unsigned long long* kept_primary;  // primaries among the kept records (ReadsMapped.num_mapped_reads, genes.rs:249-252)
   // pair path: partner of each record (cmb_pairs.cuh, records in file order) or NULL = the host layout (completed pairs
   // only, stored first mate at the even index, its partner right after)
   const int32_t* mate;
@@ -181,6 +189,86 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
     }
   }
 
+  // +1 at `s` and -1 at `e` (when e lies inside the segment) of segment `lc`, plus the chunk tail sums K1b scans
+  auto add_events = [&](uint32_t lc, uint32_t s, uint64_t e) {
+    const uint32_t L = a.len[lc];
+    const uint64_t base = (uint64_t)a.off_span[lc] * SPAN;
+    const uint64_t end_padded = (uint64_t)a.off_span[lc + 1] * SPAN;  // first element of the next segment
+    const uint64_t gs = base + s;
+    const bool has_end = e < L;  // "True unless the read hits the contig end"
+    atomicAdd(a.arena + gs, 1);
+    const uint64_t ks = gs / CHUNK;
+    const bool cont_s = end_padded > (ks + 1) * (uint64_t)CHUNK;  // this segment continues past chunk ks
+    if (has_end) {
+      const uint64_t ge = base + e;
+      atomicAdd(a.arena + ge, -1);
+      const uint64_t ke = ge / CHUNK;
+      if (ke != ks) {
+        if (cont_s) atomicAdd(a.tail_sum + ks, 1);
+        if (end_padded > (ke + 1) * (uint64_t)CHUNK) atomicAdd(a.tail_sum + ke, -1);
+      }
+    } else if (cont_s) {
+      atomicAdd(a.tail_sum + ks, 1);
+    }
+  };
+
+  if (a.gene_first) {
+    // ---- per-gene coverage (genes.rs:182-344, 467-552).  A gene's delta array is the contig's, cut to [start, end) with the
+    //      running depth at `start` as its first element: exactly what clipping every aligned block to the gene gives.  Reads
+    //      are assigned to the genes that contain their leftmost position.
+    if (keep) {
+      const bool primary = !secondary && !supplementary;
+      a.contig_seen[tid] = 1;
+      if (primary) atomicAdd(a.kept_primary, 1ull);
+      const uint32_t CL = a.contig_len[tid];
+      uint64_t ref_end = (uint32_t)pos;  // end of the last aligned block
+      for (uint32_t k = ivb; k < ive; ++k) {
+        const int32_t s = a.iv_start[k];
+        if (s == INT_MIN) continue;
+        if (s < 0 || (uint32_t)s >= CL) {  // `ups_and_downs[cursor] += 1` would panic
+          err |= ERR_BOUNDS;
+          continue;
+        }
+        ref_end = max(ref_end, (uint64_t)(uint32_t)s + (uint32_t)a.iv_len[k]);
+      }
+      const uint32_t g0 = a.gene_first[tid], g1 = a.gene_first[tid + 1];
+      if (g0 < g1 && !(err & ERR_BOUNDS)) {
+        const uint32_t maxlen = a.gene_maxlen[tid];
+        const uint32_t from = (uint32_t)pos >= maxlen ? (uint32_t)pos - maxlen + 1 : 0;  // a gene starting earlier ends at or before pos
+        uint32_t lo = g0, hi = g1;  // first gene with start >= from
+        while (lo < hi) {
+          const uint32_t mid = (lo + hi) >> 1;
+          if (a.gene_start[mid] < from) lo = mid + 1;
+          else hi = mid;
+        }
+        const uint64_t indels = (uint64_t)ins + r.del;
+        for (uint32_t g = lo; g < g1; ++g) {
+          const uint32_t gsx = a.gene_start[g], gex = a.gene_end[g];
+          if ((uint64_t)gsx >= max(ref_end, (uint64_t)(uint32_t)pos + 1)) break;  // genes are sorted by start
+          if ((uint32_t)pos >= gsx && (uint32_t)pos < gex) {  // read_starts.partition_point range (genes.rs:518-523)
+            cmb_contig_stats* row = a.rows + g;
+            atomicAdd((unsigned long long*)&row->n_records, 1ull);
+            if (primary) atomicAdd((unsigned long long*)&row->n_primary, 1ull);
+            const uint64_t mis = r.nm >= indels ? r.nm - indels : 0;  // edit.saturating_sub(indels), genes.rs:297
+            if (mis) atomicAdd((unsigned long long*)&row->sum_edit, (unsigned long long)mis);
+            if (primary && r.aligned > 0) atomicAdd(&row->sum_identity_primary, ((double)r.aligned - (double)r.nm) / (double)r.aligned);
+          }
+          for (uint32_t k = ivb; k < ive; ++k) {
+            const int32_t s = a.iv_start[k];
+            if (s == INT_MIN) continue;
+            const uint64_t e = (uint64_t)(uint32_t)s + (uint32_t)a.iv_len[k];
+            if (e <= gsx || (uint32_t)s >= gex) continue;  // no overlap
+            const uint32_t cs = max((uint32_t)s, gsx) - gsx;
+            add_events(g, cs, e - gsx);  // e - gsx >= gene length: the block runs past the gene, no -1
+          }
+        }
+      }
+    }
+    err = __reduce_or_sync(FULL, err);
+    if (err && lane == 0) atomicOr(a.error_flags, err);
+    return;
+  }
+
   const bool mine = keep && (uint32_t)tid >= a.tid_begin && (uint32_t)tid < a.tid_end;
   // ---- per-contig read counters (contig.rs:157-159, 204-211; genome.rs:173-174, 220-223, 677-682, 724-727)
   {
@@ -231,9 +319,6 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
   if (mine) {
     const uint32_t lc = (uint32_t)tid - a.tid_begin;
     const uint32_t L = a.len[lc];
-    const uint64_t base = (uint64_t)a.off_span[lc] * SPAN;
-    const uint64_t end_padded = (uint64_t)a.off_span[lc + 1] * SPAN;  // first element of the next contig
-    (void)pos;
     for (uint32_t k = ivb; k < ive; ++k) {
       const int32_t s = a.iv_start[k];
       const uint32_t n = (uint32_t)a.iv_len[k];
@@ -242,23 +327,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
         err |= ERR_BOUNDS;
         continue;
       }
-      const uint64_t gs = base + (uint32_t)s;
-      const uint64_t e = (uint64_t)(uint32_t)s + n;
-      const bool has_end = e < L;  // "True unless the read hits the contig end"
-      atomicAdd(a.arena + gs, 1);
-      const uint64_t ks = gs / CHUNK;
-      const bool cont_s = end_padded > (ks + 1) * (uint64_t)CHUNK;  // this contig continues past chunk ks
-      if (has_end) {
-        const uint64_t ge = base + e;
-        atomicAdd(a.arena + ge, -1);
-        const uint64_t ke = ge / CHUNK;
-        if (ke != ks) {
-          if (cont_s) atomicAdd(a.tail_sum + ks, 1);
-          if (end_padded > (ke + 1) * (uint64_t)CHUNK) atomicAdd(a.tail_sum + ke, -1);
-        }
-      } else if (cont_s) {
-        atomicAdd(a.tail_sum + ks, 1);
-      }
+      add_events(lc, (uint32_t)s, (uint64_t)(uint32_t)s + n);
     }
   }
   err = __reduce_or_sync(FULL, err);

@@ -28,6 +28,7 @@ struct K3Args {
   unsigned long long* pair_count;
   uint64_t pair_capacity;
   uint32_t want_csr;
+  uint32_t all_rows;  // gene mode: a gene is covered by reads that start before it, so "no record counted here" does not mean "empty"
   uint32_t* error_flags;
 };
 
@@ -38,7 +39,7 @@ __global__ void __launch_bounds__(K3_THREADS) k3_finalize(const K3Args a) {
   const uint32_t lc = blockIdx.x * K3_WARPS + warp;
   if (lc >= a.n_local) return;
   cmb_contig_stats* row = a.rows + a.tid_begin + lc;
-  if (row->n_records == 0) return;  // unseen contig: the host never consults its histogram
+  if (row->n_records == 0 && !a.all_rows) return;  // unseen contig: the host never consults its histogram
   const uint32_t L = a.len[lc];
   const uint64_t E = a.excl;
   if (!(2 * E < L)) return;  // no window (EST:436-445)

@@ -3,7 +3,8 @@
 // Mirrors the reference's CLI surface for this path: flag names and defaults from src/cli.rs:1670-2582
 // (genome :1670-2263, contig :2265-2582), FilterParameters (coverm.rs:1648-1704), EstimatorsAndTaker
 // (coverm.rs:1315-1520), parse_percentage (coverm.rs:1296-1312), run_contig / run_genome (coverm.rs:2088-2131,
-// 1539-1628).  Read mapping, sharded BAMs, dereplication, --gff and FASTA genome definitions are out of scope.
+// 1539-1628), per-gene coverage with --gff (coverm.rs:488-509, 1554-1590).  Read mapping, sharded BAMs, dereplication and
+// FASTA genome definitions are out of scope.
 //
 // Library-level switches (they expose the constructor arguments the reference's unit tests use directly;
 // contig.rs:290-322, genome.rs:940-1086):  --lib-estimators SPEC;SPEC  --lib-streaming  --lib-flags I,S,SEC
@@ -31,7 +32,7 @@ struct CliOptions {
   float min_covered_fraction = 0.0f, trim_min = 5.0f, trim_max = 95.0f;
   uint64_t contig_end_exclusion = 75;
   std::string output_format = "dense";
-  std::optional<std::string> output_file, separator, genome_definition, lib_estimators, lib_flags;
+  std::optional<std::string> output_file, separator, genome_definition, lib_estimators, lib_flags, gff, gff_feature_type;
   bool single_genome = false, lib_streaming = false, print_reads_mapped = false, timing = false, quiet = false;
   int threads = 1;
   int device = 0;
@@ -106,6 +107,8 @@ inline CliOptions parse_cli(const std::vector<std::string>& args) {
     else if ((a == "-s" || a == "--separator") && o.sub == "genome") o.separator = value();
     else if (a == "--single-genome" && o.sub == "genome") o.single_genome = true;
     else if (a == "--genome-definition" && o.sub == "genome") o.genome_definition = value();
+    else if (a == "--gff") o.gff = value();
+    else if (a == "--gff-feature-type") o.gff_feature_type = value();
     else if (a == "-t" || a == "--threads") o.threads = std::stoi(value());
     else if (a == "--device") o.device = std::stoi(value());
     else if (a == "--gpus") o.gpus = std::max(1, std::stoi(value()));
@@ -328,7 +331,13 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
       for (auto& e : plan.estimators)
         for (auto& h : e.column_headers()) headers.push_back(h);
       for (size_t i : plan.columns_to_normalise) headers[i] = "Relative Abundance (%)";
-      plan.printer.print_headers(o.sub == "contig" ? "Contig" : "Genome", headers, *os);
+      // entry type: coverm.rs:67-74 (genome), 513-520 (contig)
+      plan.printer.print_headers(o.sub == "contig" ? (o.gff ? "Gene\tContig" : "Contig") : (o.gff ? "Gene\tContig\tGenome" : "Genome"), headers, *os);
+    }
+    std::optional<GeneDefinitions> gene_definitions;
+    if (o.gff) {
+      if (o.sub == "contig" && wants_metabat(o)) throw ExitError(1, "The metabat method cannot be used with --gff");
+      gene_definitions = read_gff(*o.gff, o.gff_feature_type);
     }
     std::unique_ptr<DeviceSession> own;
     DeviceSession* session = shared_session;
@@ -340,7 +349,8 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
     const double t_driver0 = now_s();
     DriverIO io{session, plan.params, &res.timings, &res.record_counts, o.quiet ? nullptr : &err};
     if (o.sub == "contig") {
-      res.reads_mapped = contig_coverage(inputs, taker, plan.estimators, !o.no_zeros, io);
+      if (gene_definitions) res.reads_mapped = gene_coverage(inputs, taker, plan.estimators, *gene_definitions, nullptr, !o.no_zeros, io);
+      else res.reads_mapped = contig_coverage(inputs, taker, plan.estimators, !o.no_zeros, io);
     } else {
       std::optional<uint8_t> separator;  // parse_separator (coverm.rs:1522-1537)
       if (o.single_genome) separator = (uint8_t)'0';
@@ -348,7 +358,28 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
         if (o.separator->size() != 1) usage("invalid value '" + *o.separator + "' for '--separator <separator>': too many characters in string");
         separator = (uint8_t)(*o.separator)[0];
       }
-      if (separator || o.single_genome) {
+      if (gene_definitions) {  // coverm.rs:1554-1590: single-genome and separator modes win over a genome definition file
+        GenomesAndContigs gc;
+        GenomeNamer namer;
+        if (o.single_genome) namer = [](const std::string&) { return std::optional<std::string>("genome1"); };
+        else if (separator) {
+          const char sep = (char)*separator;
+          namer = [sep](const std::string& contig) -> std::optional<std::string> {
+            const size_t at = contig.find(sep);
+            if (at == std::string::npos) return std::nullopt;
+            return contig.substr(0, at);
+          };
+        } else {
+          if (!o.genome_definition) usage("a genome definition (--separator, --single-genome or --genome-definition) is required when using --gff in genome mode");
+          gc = read_genome_definition_file(*o.genome_definition);
+          namer = [&gc](const std::string& contig) -> std::optional<std::string> {
+            auto it = gc.contig_to_genome.find(contig);
+            if (it == gc.contig_to_genome.end()) return std::nullopt;
+            return gc.genomes[it->second];
+          };
+        }
+        res.reads_mapped = gene_coverage(inputs, taker, plan.estimators, *gene_definitions, &namer, !o.no_zeros, io);
+      } else if (separator || o.single_genome) {
         res.reads_mapped = mosdepth_genome_coverage(inputs, *separator, taker, !o.no_zeros, plan.estimators, o.single_genome, io);
       } else {
         if (!o.genome_definition)

@@ -236,6 +236,72 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
   return reads_mapped_vector;
 }
 
+// ---------------------------------------------------------------------------------------------- genes.rs:182-344
+// Per-gene coverage.  The device laid its arena out over the genes (cmb_set_genes) and clipped every aligned block to the genes
+// it overlaps, so each row already holds what emit_genes_for_contig (genes.rs:467-552) computes from the contig's arrays: the
+// gene's own window statistics / histogram, the primaries whose leftmost position lies in the gene, their substitutions
+// (NM.saturating_sub(indels)) and identities.  What remains is the reference's emission order and zero handling.
+inline std::vector<ReadsMapped> gene_coverage(const std::vector<InputSpec>& bam_readers, CoverageTaker& coverage_taker,
+                                              std::vector<CoverageEstimator>& coverage_estimators, const GeneDefinitions& gene_definitions,
+                                              const GenomeNamer* genome_namer, bool print_zero_coverage_genes, const DriverIO& io) {
+  std::vector<ReadsMapped> reads_mapped_vector;
+  const bool csr = io.params.want & CMB_WANT_HIST_CSR;
+  io.session->set_gene_definitions(&gene_definitions, genome_namer);
+  struct Restore {
+    DeviceSession* s;
+    ~Restore() { s->set_gene_definitions(nullptr, nullptr); }
+  } restore{io.session};
+  const std::vector<uint64_t> contig_mode_unobserved{0};  // calculate_coverage(&[0]), genes.rs:536-539
+  for (const InputSpec& in : bam_readers) {
+    const SampleResult r = run_sample(io, in);
+    coverage_taker.start_stoit(r.stoit_name);
+    const ResolvedGenes& genes = *r.genes;
+    const uint32_t n = (uint32_t)r.header().names.size();
+    std::vector<float> coverages(coverage_estimators.size());
+    for (uint32_t tid = 0; tid < n; ++tid) {
+      const uint32_t g0 = genes.first_of_tid[tid], g1 = genes.first_of_tid[tid + 1];
+      if (g0 == g1) continue;
+      if (!r.contig_seen[tid]) {  // emit_zero_coverage_genes (genes.rs:554-568)
+        if (!print_zero_coverage_genes) continue;
+        for (uint32_t g = g0; g < g1; ++g) {
+          coverage_taker.start_entry(g, genes.entries[g].name);
+          for (auto& e : coverage_estimators) e.print_zero_coverage(coverage_taker, (uint64_t)(genes.entries[g].end - genes.entries[g].start));
+          coverage_taker.finish_entry();
+        }
+        continue;
+      }
+      for (uint32_t g = g0; g < g1; ++g) {  // emit_genes_for_contig (genes.rs:502-551)
+        const cmb_contig_stats& st = r.rows[g];
+        ContigObservation ob;
+        ob.len = genes.entries[g].end - genes.entries[g].start;
+        ob.stats = &st;
+        ob.num_mapped_reads = st.n_primary;
+        ob.total_mismatches = st.sum_edit - st.sum_indel;  // sum_indel is 0: the device already summed the saturated differences
+        ob.sum_identity = st.sum_identity_primary;
+        if (csr) {
+          ob.hist = st.hist_count ? r.pairs.data() + st.hist_offset : no_pairs();
+          ob.n_hist = st.hist_count;
+        }
+        bool has_nonzero = false;
+        for (size_t k = 0; k < coverage_estimators.size(); ++k) {
+          coverage_estimators[k].add_contig(ob);
+          coverages[k] = coverage_estimators[k].calculate_coverage(contig_mode_unobserved);
+          has_nonzero = has_nonzero || coverages[k] > 0.0f;
+        }
+        if (print_zero_coverage_genes || has_nonzero) {
+          coverage_taker.start_entry(g, genes.entries[g].name);
+          for (size_t k = 0; k < coverage_estimators.size(); ++k) coverage_estimators[k].print_coverage(coverages[k], coverage_taker);
+          coverage_taker.finish_entry();
+        }
+        for (auto& e : coverage_estimators) e.setup();
+      }
+    }
+    reads_mapped_vector.push_back({r.kept_primary, r.num_detected_primary_alignments});
+    log_reads_mapped(io, r.stoit_name, reads_mapped_vector.back(), true);
+  }
+  return reads_mapped_vector;
+}
+
 // ---------------------------------------------------------------------------------------------- genome.rs:17-322
 inline std::vector<ReadsMapped> mosdepth_genome_coverage_with_contig_names(
     const std::vector<InputSpec>& bam_readers, const GenomesAndContigs& contigs_and_genomes, CoverageTaker& coverage_taker,

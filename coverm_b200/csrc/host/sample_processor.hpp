@@ -7,6 +7,7 @@
 
 #include "bam_source.hpp"
 #include "decode_runner.hpp"
+#include "genes.hpp"
 #include "shard_range.hpp"
 
 namespace cmbh {
@@ -44,6 +45,10 @@ struct SampleResult {
   uint64_t num_detected_primary_alignments = 0;  // bam_generator.rs:113-119 / filter.rs:94-96,129-131
   uint64_t n_records = 0;                        // every record read from the file
   SampleTiming timing;
+  // gene mode (--gff): rows are per gene (genes->entries order)
+  std::shared_ptr<const ResolvedGenes> genes;
+  std::vector<uint8_t> contig_seen;  // per tid: a record that passed the filters mapped here
+  uint64_t kept_primary = 0;         // primaries among those records (genes.rs:249-252)
 };
 
 [[noreturn]] inline void throw_device_error(cmb_ctx* ctx, int rc) {
@@ -200,6 +205,15 @@ class DeviceSession {
 
   // Restrict this session to the contig shard [begin, end) (multi-GPU); (0, UINT32_MAX) = everything.
   void set_shard(uint32_t begin, uint32_t end) { shard_begin_ = begin; shard_end_ = end; ref_lens_.clear(); }
+
+  // Per-gene coverage: the following samples report one row per gene of `defs` (resolved against each sample's header)
+  // instead of one per contig; nullptr returns to contig rows.
+  void set_gene_definitions(const GeneDefinitions* defs, const GenomeNamer* namer) {
+    gene_defs_ = defs;
+    gene_namer_ = namer;
+    ref_lens_.clear();
+    gene_cache_.reset();
+  }
 
   // Makes this session rank `rank` of `n_ranks` that process every sample TOGETHER (contigs range-partitioned by summed
   // length, each rank decoding only its BGZF block range, one gather of the per-contig table).  The ranks
@@ -458,7 +472,21 @@ class DeviceSession {
     }
     res.timing.tid_begin = sb;
     res.timing.tid_end = se;
-    if (res.hdr->lens != ref_lens_ || sb != ref_sb_ || se != ref_se_) {
+    uint32_t n_rows = n_ref;
+    if (gene_defs_) {
+      if (shard) throw ExitError(1, "--gff is not available together with --gpus (per-gene coverage runs on one GPU)");
+      if (!gene_cache_ || res.hdr->lens != ref_lens_ || res.hdr->names != gene_cache_names_) {
+        gene_cache_ = std::make_shared<ResolvedGenes>(resolve_genes_against_header(*gene_defs_, *res.hdr, gene_namer_));
+        gene_cache_names_ = res.hdr->names;
+        std::vector<cmb_gene> genes(gene_cache_->entries.size());
+        for (size_t g = 0; g < genes.size(); ++g) genes[g] = cmb_gene{gene_cache_->entries[g].tid, gene_cache_->entries[g].start, gene_cache_->entries[g].end};
+        rc = cmb_set_genes(ctx_, n_ref, res.hdr->lens.data(), (uint32_t)genes.size(), genes.data());
+        if (rc) throw_device_error(ctx_, rc);
+        ref_lens_ = res.hdr->lens;
+      }
+      res.genes = gene_cache_;
+      n_rows = std::max<uint32_t>(1, (uint32_t)gene_cache_->entries.size());
+    } else if (res.hdr->lens != ref_lens_ || sb != ref_sb_ || se != ref_se_) {
       ref_sb_ = sb;
       ref_se_ = se;
       rc = cmb_set_reference(ctx_, n_ref, res.hdr->lens.data(), sb, se);
@@ -690,7 +718,7 @@ class DeviceSession {
     }
     const double t_dec = now_s();
     submit();
-    ensure_rows(n_ref);
+    ensure_rows(n_rows);
     res.rows = rows_buf_;
     uint64_t n_pairs = 0;
     if (shard && group_nccl_) {
@@ -710,6 +738,11 @@ class DeviceSession {
         shard->n_pairs = n_pairs;
         local_pairs_ = res.pairs;
       }
+    }
+    if (gene_defs_) {
+      res.contig_seen.assign((size_t)n_ref + 1, 0);
+      rc = cmb_fetch_gene_extras(ctx_, res.contig_seen.data(), &res.kept_primary);
+      if (rc) throw_device_error(ctx_, rc);
     }
     cmb_get_timing(ctx_, &res.timing.device);
     if (!res.timing.device_decode) res.timing.h2d_bytes = 40ull * res.timing.device.n_records + 4 + 8ull * res.timing.device.n_intervals;
@@ -732,6 +765,10 @@ class DeviceSession {
   uint32_t shard_begin_ = 0, shard_end_ = 0xffffffffu;
   std::vector<uint64_t> ref_lens_;
   uint32_t ref_sb_ = 0, ref_se_ = 0;
+  const GeneDefinitions* gene_defs_ = nullptr;
+  const GenomeNamer* gene_namer_ = nullptr;
+  std::shared_ptr<ResolvedGenes> gene_cache_;
+  std::vector<std::string> gene_cache_names_;
   // group (multi-GPU contig sharding)
   int group_rank_ = 0, group_n_ = 1;
   bool group_nccl_ = false;

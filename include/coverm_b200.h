@@ -182,6 +182,25 @@ int cmb_set_reference(cmb_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_l
                       uint32_t tid_end);
 int cmb_set_params(cmb_ctx* ctx, const cmb_params* params, cmb_filter_mode* mode_out);
 
+/* Per-gene coverage (`--gff`; gene_coverage, src/genes.rs:182-344): instead of whole contigs the segments are genes --
+ * sub-ranges [start, end) of contigs, possibly overlapping.  The reference cuts each gene's delta array out of its contig's
+ * with the running depth at `start` as first element (genes.rs:509-514) and assigns reads to the genes containing their
+ * leftmost position (genes.rs:516-523); here every aligned block is clipped to each gene it overlaps, which yields the same
+ * arrays, and the usual scan / reductions run over the genes.  Call INSTEAD of cmb_set_reference; records keep carrying contig
+ * tids.  `genes` must be sorted by (tid, start) with start < end <= contig_len[tid].  Result rows (cmb_end_sample): one per
+ * gene, in that order, with n_primary = primaries starting in the gene, sum_edit = sum of NM.saturating_sub(indels)
+ * (genes.rs:297; sum_indel stays 0), sum_identity_primary, and the window / histogram statistics of the gene's own length. */
+typedef struct cmb_gene {
+  uint32_t tid;
+  uint32_t start;
+  uint32_t end;
+} cmb_gene;
+int cmb_set_genes(cmb_ctx* ctx, uint32_t n_contigs, const uint64_t* contig_len, uint32_t n_genes, const cmb_gene* genes);
+/* After cmb_end_sample in gene mode: contig_seen[tid] = 1 when a record that passed every filter mapped to contig tid (its
+ * genes are reported through the estimators, the others as zero-coverage entries, genes.rs:434-465); *n_kept_primary =
+ * primary alignments among those records (ReadsMapped.num_mapped_reads, genes.rs:249-252). */
+int cmb_fetch_gene_extras(cmb_ctx* ctx, uint8_t* contig_seen, uint64_t* n_kept_primary);
+
 /* One BAM file ("stoit", contig.rs:22-27). */
 int cmb_begin_sample(cmb_ctx* ctx);
 int cmb_acquire_batch(cmb_ctx* ctx, cmb_read_batch* batch);                       /* blocks until a staging batch is free */

@@ -37,7 +37,7 @@ struct Args {
   float min_covered_fraction = 0.0f, trim_min = 5.0f, trim_max = 95.0f;
   uint64_t contig_end_exclusion = 75;
   std::string output_format = "dense";
-  std::optional<std::string> output_file, separator, genome_definition;
+  std::optional<std::string> output_file, separator, genome_definition, gff, gff_feature_type;
   bool single_genome = false;
   int threads = 1;
   // library-level
@@ -101,6 +101,8 @@ Args parse_args(int argc, char** argv) {
     else if (s == "-s" || s == "--separator") a.separator = val();
     else if (s == "--single-genome") a.single_genome = true;
     else if (s == "--genome-definition") a.genome_definition = val();
+    else if (s == "--gff") a.gff = val();
+    else if (s == "--gff-feature-type") a.gff_feature_type = val();
     else if (s == "-t" || s == "--threads") a.threads = std::stoi(val());
     else if (s == "--lib-estimators") a.lib_estimators = val();
     else if (s == "--lib-flags") a.lib_flags = val();
@@ -350,15 +352,23 @@ int run(int argc, char** argv, std::ostream& out_default) {
   for (auto& p : a.bam_files) stoits.push_back(file_stem(p));
   if (a.sub == "contig") {
     FilterParameters fp = filter_params_from(a, true);
+    std::optional<GeneDefinitions> gene_definitions;  // coverm.rs:488-509
+    if (a.gff) {
+      if (doing_metabat(a)) throw ExitError(1, "The metabat method cannot be used with --gff");
+      gene_definitions = read_gff(*a.gff, a.gff_feature_type);
+    }
     EstimatorsAndTaker et = generate_estimators(a, os);
-    if (!a.lib_streaming) print_headers(et, "Contig", *os);
+    if (!a.lib_streaming) print_headers(et, gene_definitions ? "Gene\tContig" : "Contig", *os);
     auto readers = make_readers(a, fp);
-    reads_mapped = contig_coverage(readers, et.taker, et.estimators, !a.no_zeros, fp.flag_filters);
+    if (gene_definitions)  // run_contig, coverm.rs:2100-2111
+      reads_mapped = gene_coverage(readers, et.taker, et.estimators, *gene_definitions, nullptr, !a.no_zeros, fp.flag_filters);
+    else
+      reads_mapped = contig_coverage(readers, et.taker, et.estimators, !a.no_zeros, fp.flag_filters);
     et.printer.finalise_printing(et.taker, *os, &reads_mapped, et.columns_to_normalise, et.rpkm_column, et.tpm_column);
   } else if (a.sub == "genome") {
     FilterParameters fp = filter_params_from(a, false);
     EstimatorsAndTaker et = generate_estimators(a, os);
-    if (!a.lib_streaming) print_headers(et, "Genome", *os);
+    if (!a.lib_streaming) print_headers(et, a.gff ? "Gene\tContig\tGenome" : "Genome", *os);  // coverm.rs:67-74
     // parse_separator, coverm.rs:1522-1537
     std::optional<uint8_t> separator;
     if (a.single_genome) separator = (uint8_t)'0';
@@ -367,7 +377,29 @@ int run(int argc, char** argv, std::ostream& out_default) {
       separator = (uint8_t)(*a.separator)[0];
     }
     auto readers = make_readers(a, fp);
-    if (separator.has_value() || a.single_genome) {
+    if (a.gff) {  // coverm.rs:1554-1590: per-gene coverage with a genome column; separator / single-genome win over the definition file
+      const GeneDefinitions gene_definitions = read_gff(*a.gff, a.gff_feature_type);
+      GenomesAndContigs gc;
+      GenomeNamer namer;
+      if (a.single_genome) namer = [](const std::string&) { return std::optional<std::string>("genome1"); };
+      else if (separator) {
+        const char sep = (char)*separator;
+        namer = [sep](const std::string& contig) -> std::optional<std::string> {
+          const size_t at = contig.find(sep);
+          if (at == std::string::npos) return std::nullopt;
+          return contig.substr(0, at);
+        };
+      } else {
+        if (!a.genome_definition) usage_error("a genome definition is required when using --gff in genome mode");
+        gc = read_genome_definition_file(*a.genome_definition);
+        namer = [&gc](const std::string& contig) -> std::optional<std::string> {
+          auto it = gc.contig_to_genome.find(contig);
+          if (it == gc.contig_to_genome.end()) return std::nullopt;
+          return gc.genomes[it->second];
+        };
+      }
+      reads_mapped = gene_coverage(readers, et.taker, et.estimators, gene_definitions, &namer, !a.no_zeros, fp.flag_filters);
+    } else if (separator.has_value() || a.single_genome) {
       reads_mapped = mosdepth_genome_coverage(readers, *separator, et.taker, !a.no_zeros, et.estimators,
                                               fp.flag_filters, a.single_genome);
     } else {

@@ -36,6 +36,13 @@ struct cmb_ctx {
   std::vector<cmb_hist_pair> pairs;
   int64_t last_kept_tid = INT64_MIN;
   int64_t excl_min = INT64_MAX, excl_max = INT64_MIN;  // kept tid range of the exclusive records (cmb_kept_tid_range)
+  // gene mode (cmb_set_genes): lens / rows / arena are per gene; records carry contig tids
+  bool gene_mode = false;
+  std::vector<uint64_t> contig_lens;
+  std::vector<cmb_gene> genes;
+  std::vector<uint32_t> gene_first;
+  std::vector<uint8_t> contig_seen;
+  uint64_t kept_primary = 0;
   int error = 0;
   uint64_t n_records = 0, n_intervals = 0;
 };
@@ -79,8 +86,29 @@ void cmb_destroy(cmb_ctx* c) { delete c; }
 
 int cmb_set_reference(cmb_ctx* c, uint32_t n, const uint64_t* len, uint32_t b, uint32_t e) {
   c->lens.assign(len, len + n);
+  c->gene_mode = false;
   c->tid_begin = b;
   c->tid_end = e;
+  return CMB_OK;
+}
+
+int cmb_set_genes(cmb_ctx* c, uint32_t n_contigs, const uint64_t* contig_len, uint32_t n_genes, const cmb_gene* genes) {
+  c->gene_mode = true;
+  c->contig_lens.assign(contig_len, contig_len + n_contigs);
+  c->genes.assign(genes, genes + n_genes);
+  c->gene_first.assign((size_t)n_contigs + 1, 0);
+  for (uint32_t g = 0; g < n_genes; ++g) c->gene_first[genes[g].tid + 1] += 1;
+  for (uint32_t t = 0; t < n_contigs; ++t) c->gene_first[t + 1] += c->gene_first[t];
+  c->lens.clear();
+  for (uint32_t g = 0; g < n_genes; ++g) c->lens.push_back(genes[g].end - genes[g].start);
+  if (c->lens.empty()) c->lens.push_back(1);
+  c->tid_begin = 0;
+  c->tid_end = (uint32_t)c->lens.size();
+  return CMB_OK;
+}
+int cmb_fetch_gene_extras(cmb_ctx* c, uint8_t* contig_seen, uint64_t* n_kept_primary) {
+  if (!c->contig_seen.empty()) memcpy(contig_seen, c->contig_seen.data(), c->contig_seen.size());
+  *n_kept_primary = c->kept_primary;
   return CMB_OK;
 }
 
@@ -103,6 +131,8 @@ int cmb_begin_sample(cmb_ctx* c) {
   c->last_kept_tid = INT64_MIN;
   c->excl_min = INT64_MAX;
   c->excl_max = INT64_MIN;
+  c->contig_seen.assign(c->gene_mode ? c->contig_lens.size() : 0, 0);
+  c->kept_primary = 0;
   c->error = 0;
   c->in_sample = true;
   c->ended = false;
@@ -163,12 +193,50 @@ static int submit(cmb_ctx* c, const cmb_read_batch& b, uint32_t n, uint32_t ni, 
     if (nm_err) c->error |= 2;
     if (!keep) continue;
     const int32_t tid = b.tid[i];
-    if (tid < 0 || (size_t)tid >= c->lens.size()) { c->error |= 4; continue; }
+    if (tid < 0 || (size_t)tid >= (c->gene_mode ? c->contig_lens.size() : c->lens.size())) { c->error |= 4; continue; }
     if (tid < c->last_kept_tid) c->error |= 1;
     c->last_kept_tid = std::max<int64_t>(c->last_kept_tid, tid);
     if (i < excl_n) {
       c->excl_min = std::min<int64_t>(c->excl_min, tid);
       c->excl_max = std::max<int64_t>(c->excl_max, tid);
+    }
+    if (c->gene_mode) {
+      // genes.rs:254-303 + 467-552 restated per gene: the gene's array is the contig's cut to [start, end) with the running
+      // depth at `start` in front, i.e. every aligned block clipped to the gene; reads count for the genes holding their pos
+      const bool primary = !sec && !sup;
+      c->contig_seen[tid] = 1;
+      c->kept_primary += primary;
+      const uint64_t CL = c->contig_lens[tid];
+      bool bad = false;
+      for (uint32_t k = b.iv_begin[i]; k < b.iv_begin[i + 1]; ++k) {
+        const int32_t s = b.iv_start[k];
+        if (s == CMB_IV_PAD) continue;
+        if (s < 0 || (uint64_t)s >= CL) { c->error |= 4; bad = true; }
+      }
+      if (bad) continue;
+      const uint64_t indels = (uint64_t)b.ins[i] + r.del;
+      for (uint32_t g = c->gene_first[tid]; g < c->gene_first[tid + 1]; ++g) {
+        const cmb_gene& ge = c->genes[g];
+        cmb_contig_stats& row = c->rows[g];
+        if ((uint32_t)b.pos[i] >= ge.start && (uint32_t)b.pos[i] < ge.end) {
+          row.n_records += 1;
+          row.n_primary += primary;
+          row.sum_edit += r.nm >= indels ? r.nm - indels : 0;
+          if (primary && r.aligned > 0) row.sum_identity_primary += ((double)r.aligned - (double)r.nm) / (double)r.aligned;
+        }
+        for (uint32_t k = b.iv_begin[i]; k < b.iv_begin[i + 1]; ++k) {
+          const int32_t s = b.iv_start[k];
+          if (s == CMB_IV_PAD) continue;
+          const uint64_t e = (uint64_t)s + (uint32_t)b.iv_len[k];
+          if (e <= ge.start || (uint32_t)s >= ge.end) continue;
+          auto& ud = c->arena[g];
+          const uint64_t L = ge.end - ge.start;
+          if (ud.empty()) ud.assign(L + 1, 0);
+          ud[std::max<uint32_t>((uint32_t)s, ge.start) - ge.start] += 1;
+          if (e - ge.start < L) ud[e - ge.start] -= 1;
+        }
+      }
+      continue;
     }
     if ((uint32_t)tid < c->tid_begin || (uint32_t)tid >= c->tid_end) continue;
     cmb_contig_stats& row = c->rows[tid];
@@ -412,6 +480,13 @@ int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** out) {
   c->in_sample = false;
   const uint64_t E = c->p.contig_end_exclusion;
   const bool hist = c->p.want & (CMB_WANT_HIST | CMB_WANT_HIST_CSR), csr = c->p.want & CMB_WANT_HIST_CSR;
+  if (c->gene_mode)  // every gene of a seen contig is scanned, covered or not (the device scans the whole arena)
+    for (size_t t = 0; t < c->contig_seen.size(); ++t)
+      if (c->contig_seen[t])
+        for (uint32_t g = c->gene_first[t]; g < c->gene_first[t + 1]; ++g) {
+          auto& ud = c->arena[g];
+          if (ud.empty()) ud.assign(c->lens[g] + 1, 0);
+        }
   for (auto& kv : c->arena) {
     const uint32_t tid = kv.first;
     const uint64_t L = c->lens[tid];
@@ -428,7 +503,7 @@ int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** out) {
         if (hist) h[(uint32_t)d] += 1;
       }
     }
-    if (!hist || !win || row.n_records == 0) continue;
+    if (!hist || !win || (row.n_records == 0 && !c->gene_mode)) continue;  // a gene may be covered by reads that start before it
     const uint64_t T = L - 2 * E;
     const uint64_t min_index = (uint64_t)std::floor(c->p.trim_min * (float)T), max_index = (uint64_t)std::ceil(c->p.trim_max * (float)T);
     uint64_t cprev = 0, total = 0, s0 = 0, s1 = 0, s2 = 0, k = h.begin()->first;

@@ -903,6 +903,282 @@ inline std::vector<ReadsMapped> contig_coverage(std::vector<ReaderFactory>& bam_
   return reads_mapped_vector;
 }
 
+// ---------------------------------------------------------------- genes.rs
+struct Gene {  // genes.rs:16-25
+  std::string id, contig;
+  uint64_t start = 0, end = 0;  // 0-based, half-open
+};
+struct GeneDefinitions {
+  std::vector<Gene> genes;
+};
+
+inline std::string rust_trim(const std::string& x) {  // str::trim: Unicode White_Space; the ASCII members suffice here
+  size_t a = 0, b = x.size();
+  auto ws = [](unsigned char c) { return c == ' ' || (c >= 9 && c <= 13); };
+  while (a < b && ws((unsigned char)x[a])) ++a;
+  while (b > a && ws((unsigned char)x[b - 1])) --b;
+  return x.substr(a, b - a);
+}
+
+// genes.rs:146-164: `key=value` (GFF3) or `key "value"` (GTF) among the `;`-separated attributes
+inline std::optional<std::string> parse_gff_attribute(const std::string& attributes, const std::string& key) {
+  size_t a = 0;
+  for (;;) {
+    size_t b = attributes.find(';', a);
+    std::string entry = rust_trim(attributes.substr(a, b == std::string::npos ? std::string::npos : b - a));
+    if (!entry.empty()) {
+      if (entry.compare(0, key.size() + 1, key + "=") == 0) return rust_trim(entry.substr(key.size() + 1));
+      if (entry.compare(0, key.size() + 1, key + " ") == 0) {
+        std::string v = rust_trim(entry.substr(key.size() + 1));
+        size_t x = 0, y = v.size();
+        while (x < y && v[x] == '"') ++x;
+        while (y > x && v[y - 1] == '"') --y;
+        return v.substr(x, y - x);
+      }
+    }
+    if (b == std::string::npos) break;
+    a = b + 1;
+  }
+  return std::nullopt;
+}
+inline std::optional<std::string> parse_gff_id(const std::string& attributes) {  // genes.rs:131-142
+  for (const char* key : {"ID", "locus_tag", "gene_id", "Name", "gene", "Parent"}) {
+    auto v = parse_gff_attribute(attributes, key);
+    if (v && !v->empty()) return v;
+  }
+  return std::nullopt;
+}
+
+// GeneDefinitions::read_gff, genes.rs:44-126
+inline GeneDefinitions read_gff(const std::string& path, const std::optional<std::string>& feature_type) {
+  FILE* f = fopen(path.c_str(), "rb");
+  if (!f) throw Panic("Failed to open GFF file " + path);
+  std::string text;
+  char chunk[1 << 16];
+  size_t got;
+  while ((got = fread(chunk, 1, sizeof chunk, f)) > 0) text.append(chunk, got);
+  fclose(f);
+  GeneDefinitions defs;
+  uint64_t auto_id = 0;
+  size_t a = 0;
+  while (a < text.size()) {
+    size_t b = text.find('\n', a);
+    if (b == std::string::npos) b = text.size();
+    std::string line = text.substr(a, b - a);
+    a = b + 1;
+    if (!line.empty() && line.back() == '\r') line.pop_back();  // BufRead::lines strips "\r\n"
+    {  // trim_end
+      size_t e = line.size();
+      while (e > 0 && (line[e - 1] == ' ' || ((unsigned char)line[e - 1] >= 9 && (unsigned char)line[e - 1] <= 13))) --e;
+      line.resize(e);
+    }
+    if (line.empty() || line[0] == '#') continue;
+    std::vector<std::string> fields;
+    {
+      size_t x = 0;
+      for (;;) {
+        size_t y = line.find('\t', x);
+        if (y == std::string::npos) { fields.push_back(line.substr(x)); break; }
+        fields.push_back(line.substr(x, y - x));
+        x = y + 1;
+      }
+    }
+    if (fields.size() < 8) continue;  // warn!: malformed line
+    if (feature_type && fields[2] != *feature_type) continue;
+    auto parse_u64 = [](const std::string& t, uint64_t& v) {  // str::parse::<u64>: optional '+', digits only, no overflow
+      size_t i = 0;
+      if (!t.empty() && t[0] == '+') i = 1;
+      if (i >= t.size()) return false;
+      unsigned __int128 acc = 0;
+      for (; i < t.size(); ++i) {
+        if (t[i] < '0' || t[i] > '9') return false;
+        acc = acc * 10 + (unsigned)(t[i] - '0');
+        if (acc > (unsigned __int128)UINT64_MAX) return false;
+      }
+      v = (uint64_t)acc;
+      return true;
+    };
+    uint64_t start_1based, end_1based;
+    if (!parse_u64(fields[3], start_1based)) continue;
+    if (!parse_u64(fields[4], end_1based)) continue;
+    if (start_1based == 0 || end_1based < start_1based) continue;
+    const std::string attributes = fields.size() > 8 ? fields[8] : std::string();
+    Gene g;
+    g.contig = fields[0];
+    auto id = parse_gff_id(attributes);
+    if (id) g.id = *id;
+    else {
+      auto_id += 1;
+      g.id = g.contig + "_gene_" + std::to_string(auto_id);
+    }
+    g.start = start_1based - 1;
+    g.end = end_1based;
+    defs.genes.push_back(g);
+  }
+  return defs;
+}
+
+struct ResolvedGene {  // genes.rs:168-173
+  size_t entry_id = 0;
+  std::string name;
+  size_t start = 0, end = 0;
+};
+using GenomeNamer = std::function<std::optional<std::string>(const std::string&)>;
+
+// genes.rs:351-432
+inline std::vector<std::vector<ResolvedGene>> resolve_genes_against_header(const GeneDefinitions& defs, const Header& header,
+                                                                          const GenomeNamer* genome_namer) {
+  std::unordered_map<std::string, size_t> name_to_tid;
+  for (size_t tid = 0; tid < header.names.size(); ++tid) name_to_tid[header.names[tid]] = tid;  // later duplicates win, like HashMap::insert
+  std::vector<std::vector<ResolvedGene>> genes_by_tid(header.names.size());
+  for (auto& gene : defs.genes) {
+    auto it = name_to_tid.find(gene.contig);
+    if (it == name_to_tid.end()) continue;
+    const size_t tid = it->second;
+    const uint64_t contig_len = header.lens[tid];
+    const uint64_t start = std::min(gene.start, contig_len), end = std::min(gene.end, contig_len);
+    if (start >= end) continue;
+    ResolvedGene r;
+    if (genome_namer) {
+      auto genome = (*genome_namer)(gene.contig);
+      if (!genome) continue;
+      r.name = gene.id + "\t" + gene.contig + "\t" + *genome;
+    } else {
+      r.name = gene.id + "\t" + gene.contig;
+    }
+    r.start = (size_t)start;
+    r.end = (size_t)end;
+    genes_by_tid[tid].push_back(r);
+  }
+  size_t next_entry_id = 0;
+  for (auto& genes : genes_by_tid) {
+    std::stable_sort(genes.begin(), genes.end(), [](const ResolvedGene& x, const ResolvedGene& y) { return x.start < y.start; });  // sort_by_key is stable
+    for (auto& g : genes) g.entry_id = next_entry_id++;
+  }
+  return genes_by_tid;
+}
+
+// genes.rs:467-552
+inline void emit_genes_for_contig(const std::vector<ResolvedGene>& genes, const std::vector<int32_t>& ups_and_downs,
+                                  const std::vector<uint64_t>& read_starts, const std::vector<uint64_t>& read_is_primary,
+                                  const std::vector<uint64_t>& read_mismatches, const std::vector<double>& read_identities,
+                                  std::vector<CoverageEstimator>& ests, CoverageTaker& taker, bool print_zero_coverage_genes) {
+  if (genes.empty()) return;
+  const size_t contig_len = ups_and_downs.size();
+  std::vector<int32_t> coverage_at_base(contig_len, 0);
+  int32_t running = 0;
+  for (size_t i = 0; i < contig_len; ++i) {
+    running += ups_and_downs[i];
+    coverage_at_base[i] = running;
+  }
+  const size_t n = read_starts.size();
+  std::vector<uint64_t> prefix_primary(n + 1, 0), prefix_mismatches(n + 1, 0);
+  std::vector<double> prefix_identity(n + 1, 0.0);
+  for (size_t i = 0; i < n; ++i) {
+    prefix_primary[i + 1] = prefix_primary[i] + read_is_primary[i];
+    prefix_mismatches[i + 1] = prefix_mismatches[i] + read_mismatches[i];
+    prefix_identity[i + 1] = prefix_identity[i] + read_identities[i];
+  }
+  for (auto& gene : genes) {
+    const size_t start = gene.start, end = std::min(gene.end, contig_len);
+    if (start >= end) continue;
+    const size_t len = end - start;
+    std::vector<int32_t> gene_ups_and_downs(len, 0);
+    gene_ups_and_downs[0] = coverage_at_base[start];
+    for (size_t i = 1; i < len; ++i) gene_ups_and_downs[i] = ups_and_downs[start + i];
+    // partition_point: first index whose start is not < bound (read_starts ascends within a sorted contig)
+    auto pp = [&](size_t bound) {
+      size_t lo = 0, hi = n;
+      while (lo < hi) {
+        size_t mid = lo + (hi - lo) / 2;
+        if ((size_t)read_starts[mid] < bound) lo = mid + 1;
+        else hi = mid;
+      }
+      return lo;
+    };
+    const size_t lo = pp(start), hi = pp(end);
+    const uint64_t num_mapped_reads = prefix_primary[hi] - prefix_primary[lo];
+    const uint64_t mismatches = prefix_mismatches[hi] - prefix_mismatches[lo];
+    const double sum_identity = prefix_identity[hi] - prefix_identity[lo];
+    for (auto& e : ests) e.add_contig(gene_ups_and_downs, num_mapped_reads, mismatches, sum_identity);
+    std::vector<float> coverages;
+    for (auto& e : ests) coverages.push_back(e.calculate_coverage({0}));
+    bool has_nonzero = false;
+    for (float c : coverages) if (c > 0.0f) has_nonzero = true;
+    if (print_zero_coverage_genes || has_nonzero) {
+      taker.start_entry(gene.entry_id, gene.name);
+      for (size_t i = 0; i < coverages.size(); ++i) ests[i].print_coverage(coverages[i], taker);
+      taker.finish_entry();
+    }
+    for (auto& e : ests) e.setup();
+  }
+}
+
+// genes.rs:182-344
+inline std::vector<ReadsMapped> gene_coverage(std::vector<ReaderFactory>& bam_readers, CoverageTaker& coverage_taker,
+                                              std::vector<CoverageEstimator>& coverage_estimators, const GeneDefinitions& gene_definitions,
+                                              const GenomeNamer* genome_namer, bool print_zero_coverage_genes,
+                                              const FlagFilter& flag_filters) {
+  std::vector<ReadsMapped> reads_mapped_vector;
+  for (auto& gen : bam_readers) {
+    std::unique_ptr<NamedBamReader> bam_generated = gen();
+    coverage_taker.start_stoit(bam_generated->name());
+    const Header& header = bam_generated->header();
+    const auto genes_by_tid = resolve_genes_against_header(gene_definitions, header, genome_namer);
+    Record record;
+    int32_t last_tid = -2;
+    std::vector<int32_t> ups_and_downs;
+    std::vector<uint64_t> read_starts, read_is_primary, read_mismatches;
+    std::vector<double> read_identities;
+    uint64_t num_mapped_reads_total = 0;
+    auto process_previous_genes = [&](int32_t last_tid_, int32_t current_tid) {  // :434-465
+      if (last_tid_ != -2)
+        emit_genes_for_contig(genes_by_tid[(size_t)last_tid_], ups_and_downs, read_starts, read_is_primary, read_mismatches, read_identities,
+                              coverage_estimators, coverage_taker, print_zero_coverage_genes);
+      if (print_zero_coverage_genes) {
+        for (int32_t my_tid = last_tid_ == -2 ? 0 : last_tid_ + 1; my_tid < current_tid; ++my_tid) {
+          for (auto& gene : genes_by_tid[(size_t)my_tid]) {  // emit_zero_coverage_genes :554-568
+            coverage_taker.start_entry(gene.entry_id, gene.name);
+            for (auto& e : coverage_estimators) e.print_zero_coverage(coverage_taker, (uint64_t)(gene.end - gene.start));
+            coverage_taker.finish_entry();
+          }
+        }
+      }
+    };
+    while (bam_generated->read(record)) {
+      if (!flag_filters.passes(record)) continue;
+      if (record.is_unmapped()) continue;
+      const int32_t tid = record.tid;
+      if (tid != last_tid) {
+        if (tid < last_tid) throw Panic("BAM file appears to be unsorted.");
+        process_previous_genes(last_tid, tid);
+        if (tid < 0 || (size_t)tid >= header.lens.size()) throw Panic("Corrupt BAM file?");
+        ups_and_downs.assign((size_t)header.lens[tid], 0);
+        last_tid = tid;
+        read_starts.clear();
+        read_is_primary.clear();
+        read_mismatches.clear();
+        read_identities.clear();
+      }
+      const bool is_primary = !record.is_supplementary() && !record.is_secondary();
+      if (is_primary) num_mapped_reads_total += 1;
+      uint64_t aligned_len = 0, indels = 0;
+      accumulate_cigar(record, ups_and_downs, indels, aligned_len);
+      const uint64_t edit = nm(record);
+      read_starts.push_back((uint64_t)(int64_t)record.pos);
+      read_is_primary.push_back(is_primary ? 1 : 0);
+      read_mismatches.push_back(edit >= indels ? edit - indels : 0);  // saturating_sub
+      read_identities.push_back(is_primary && aligned_len > 0 ? ((double)aligned_len - (double)edit) / (double)aligned_len : 0.0);
+    }
+    process_previous_genes(last_tid, (int32_t)genes_by_tid.size());
+    ReadsMapped rm;
+    rm.num_mapped_reads = num_mapped_reads_total;
+    rm.num_reads = bam_generated->num_detected_primary_alignments();
+    reads_mapped_vector.push_back(rm);
+  }
+  return reads_mapped_vector;
+}
+
 // ---------------------------------------------------------------- genome.rs
 struct GenomesAndContigs {  // genomes_and_contigs.rs:7-58
   std::vector<std::string> genomes;

@@ -438,7 +438,46 @@ CLI_CASES = [
          stdout="Genome\t2seqs.bad_read.1.with_supplementary ANIr\ngenome1\t0.999\n"),
 ]
 
+# ---------------------------------------------------------------- per-gene coverage (src/genes.rs, --gff)
+# genes.rs unit tests build GeneDefinitions in code (whole-contig genes on seq1 / seq2 of the 2seqs reference);
+# 2seqs_whole_contig_genes.gff (written for these cases, not a reference file) states the same two genes as GFF lines.
+# Harness of genes.rs:577-618: streaming taker, mean(0.0, 0, false) / read-count estimator, FlagFilter {improper: true,
+# secondary: false, supplementary: false}.
+_G2 = "2seqs.reads_for_seq1"
+_WHOLE = "{D}/2seqs_whole_contig_genes.gff"
+GENE_CASES = [
+    _cli("src/genes.rs:646-679", "contig",
+         ["-b", "{D}/" + _G2 + ".bam", "--gff", _WHOLE, "--lib-streaming", "--lib-estimators", "mean:0.0:0:0", "--lib-flags", "1,0,0"],
+         stdout=f"{_G2}\tgene_seq1\tseq1\t1.2\n{_G2}\tgene_seq2\tseq2\t0\n"),
+    _cli("src/genes.rs:681-718", "genome",
+         ["-b", "{D}/" + _G2 + ".bam", "--gff", _WHOLE, "--genome-definition", "{DEF}", "--lib-streaming", "--lib-estimators", "mean:0.0:0:0",
+          "--lib-flags", "1,0,0"],
+         definition="genomeA\tseq1\n", stdout=f"{_G2}\tgene_seq1\tseq1\tgenomeA\t1.2\n"),
+    _cli("src/genes.rs:720-745", "contig",
+         ["-b", "{D}/" + _G2 + ".bam", "--gff", _WHOLE, "--lib-streaming", "--lib-estimators", "mean:0.0:0:0", "--lib-flags", "1,0,0", "--no-zeros"],
+         stdout=f"{_G2}\tgene_seq1\tseq1\t1.2\n"),
+    _cli("src/genes.rs:747-765", "contig",
+         ["-b", "{D}/" + _G2 + ".bam", "--gff", "{D}/2seqs_gene_seq1_only.gff", "--lib-streaming", "--lib-estimators", "count", "--lib-flags", "1,0,0",
+          "--no-zeros"],
+         stdout=f"{_G2}\tgene_seq1\tseq1\t12\n"),
+    _cli("tests/test_cmdline.rs:134-158", "contig",
+         ["--bam-files", "{D}/" + _G2 + ".bam", "--gff", "{D}/2seqs.gff", "--methods", "mean", "--contig-end-exclusion", "0", "--output-format", "sparse"],
+         contains=["Sample\tGene\tContig\tMean", f"{_G2}\tgene1\tseq1\t1.2", f"{_G2}\tgene3\tseq2\t0"]),
+    _cli("tests/test_cmdline.rs:160-179", "contig",
+         ["--bam-files", "{D}/" + _G2 + ".bam", "--gff", "{D}/2seqs.gff", "--methods", "count", "--output-format", "sparse", "--no-zeros"],
+         contains=[f"{_G2}\tgene1\tseq1\t12"]),
+    _cli("tests/test_cmdline.rs:181-209", "genome",
+         ["--bam-files", "{D}/" + _G2 + ".bam", "--gff", "{D}/2seqs.gff", "--genome-definition", "{D}/2seqs.genome-definition", "--methods", "mean",
+          "--contig-end-exclusion", "0", "--min-covered-fraction", "0", "--output-format", "sparse"],
+         contains=["Sample\tGene\tContig\tGenome\tMean", f"{_G2}\tgene1\tseq1\tgenomeA\t1.2", f"{_G2}\tgene3\tseq2\tgenomeB\t0"]),
+]
+OWN_GFF_FIXTURES = {  # GFF statements of the gene sets genes.rs's unit tests construct in code
+    "2seqs_whole_contig_genes.gff": "seq1\ttest\tgene\t1\t1000\t.\t+\t.\tID=gene_seq1\nseq2\ttest\tgene\t1\t1000\t.\t+\t.\tID=gene_seq2\n",
+    "2seqs_gene_seq1_only.gff": "seq1\ttest\tgene\t1\t1000\t.\t+\t.\tID=gene_seq1\n",
+}
+CLI_CASES = CLI_CASES + GENE_CASES
+
 ALL_CASES = CASES + FILTER_CASES + CLI_CASES
 
 # fixtures (under /root/reference/tests/data) the cases above read
-FIXTURES = sorted({a.split("/", 1)[1] for c in ALL_CASES for a in c["argv"] if a.startswith("{D}/")})
+FIXTURES = sorted({a.split("/", 1)[1] for c in ALL_CASES for a in c["argv"] if a.startswith("{D}/")} - set(OWN_GFF_FIXTURES))
