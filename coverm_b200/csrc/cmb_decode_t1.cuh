@@ -14,7 +14,7 @@
 // declined block gets the one-stream-per-warp kernel and finally the library's zlib.
 #pragma once
 
-constexpr uint32_t T1_THREADS = 128;  // per CTA; four CTAs per SM (452 B of tables per thread)
+constexpr uint32_t T1_THREADS = 96;   // per CTA; five CTAs per SM (452 B of tables per thread + 1 KB reserved per CTA): 15 warps
 
 struct T1Stream {           // per-thread tables; 113 words: an odd stride keeps the 32 lanes of a warp on 32 different banks
   uint8_t perm_lit_lo[288];  // literal/length symbols sorted by (code length, symbol): low 8 bits ...
@@ -45,12 +45,28 @@ struct T1Reader {  // LSB-first bit reader over global memory; two aligned words
     refill();
   }
   __device__ __forceinline__ void refill() {  // afterwards cnt >= 33
-    if (cnt <= 32) {
+    const bool take = cnt <= 32;
+    if (take) {
       buf |= (uint64_t)w0 << cnt;
       cnt += 32;
       w0 = w1;
-      w1 = __ldcg(wp++);
     }
+#ifdef __CUDA_ARCH__
+    // the new word is loaded IN PLACE into w1 under a predicate: written as `if (take) w1 = load` the compiler loads into a
+    // temporary and moves it at once, which waits for the load and defeats the prefetch (ncu: 10 % of the stall samples)
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.u32 p, %2, 0;\n"
+        "@p ld.global.cg.u32 %0, [%1];\n"
+        "}\n"
+        : "+r"(w1)
+        : "l"(wp), "r"((uint32_t)take)
+        : "memory");
+#else
+    if (take) w1 = __ldcg(wp);
+#endif
+    if (take) ++wp;
   }
   __device__ __forceinline__ void consume(uint32_t n) {
     buf >>= n;
@@ -103,7 +119,7 @@ __device__ __forceinline__ bool t1_build(LenOf len_of, uint32_t n, Put put, int1
   return ok;
 }
 
-__global__ void __launch_bounds__(T1_THREADS, 4) kd_inflate_t1(const InflateArgs a) {
+__global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs a) {
   extern __shared__ __align__(16) uint8_t t1_smem[];
   T1Stream& S = reinterpret_cast<T1Stream*>(t1_smem)[threadIdx.x];
   uint32_t lit_lim[15], dst_lim[15];
@@ -115,6 +131,20 @@ __global__ void __launch_bounds__(T1_THREADS, 4) kd_inflate_t1(const InflateArgs
   br.buf = 0;
   br.cnt = 0;
 
+  // The last short match of a thread stays PENDING: its source bytes are requested into registers and stored only when the
+  // next match (or the end of the pass) needs them done, so the DRAM / L2 latency of the LZ77 history read -- the dominant
+  // stall of this kernel, the live history of all streams is far larger than L2 -- overlaps the decoding of the next symbols.
+  uint32_t pm_len = 0;
+  uint8_t* pm_dp = nullptr;
+  uint8_t pm[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  auto flush_pending = [&]() {
+    if (pm_len) {
+#pragma unroll
+      for (uint32_t k = 0; k < 8; ++k)
+        if (k < pm_len) pm_dp[k] = pm[k];
+      pm_len = 0;
+    }
+  };
   enum : uint32_t { IDLE, WAIT, HDR, SYM, FIN };
   uint32_t state = IDLE;
   uint32_t b = 0, n_out = 0, op = 0, bfinal = 0, spins = 0;
@@ -349,7 +379,14 @@ __global__ void __launch_bounds__(T1_THREADS, 4) kd_inflate_t1(const InflateArgs
         }
         uint8_t* dp = out + op;
         const uint8_t* sp = dp - dist;
-        if (dist >= len) {  // source and destination do not overlap: eight loads in flight, then eight stores
+        flush_pending();  // this match may read what the pending one writes
+        if (len <= 8 && dist >= len) {  // the common case: request the bytes, store them later
+#pragma unroll
+          for (uint32_t k = 0; k < 8; ++k)
+            if (k < len) pm[k] = sp[k];
+          pm_len = len;
+          pm_dp = dp;
+        } else if (dist >= len) {  // source and destination do not overlap: eight loads in flight, then eight stores
           for (uint32_t i = 0; i < len; i += 8) {
             uint8_t t8[8];
 #pragma unroll
@@ -364,6 +401,7 @@ __global__ void __launch_bounds__(T1_THREADS, 4) kd_inflate_t1(const InflateArgs
         }
         op += len;
       }
+      flush_pending();
     }
     // ------------------------------------------------------------------ verdicts
     if (state == FIN && st == 0) {  // last deflate block done

@@ -58,6 +58,7 @@ namespace {
 #include "cmb_decode_g8.cuh"
 #include "cmb_decode_t1.cuh"
 #include "cmb_pairs.cuh"
+#include "cmb_filter.cuh"
 
 // rows[i].hist_offset += base for the rows that carry histogram pairs (cmb_allgather_stats: local -> global pair offsets)
 __global__ void __launch_bounds__(256) k_rebase_hist_offsets(cmb_contig_stats* rows, uint32_t n, uint64_t base) {
@@ -196,6 +197,15 @@ struct cmb_ctx {
     uint32_t* d_pair_head = nullptr;
     size_t pair_table_cap = 0;
     const int32_t* last_mate = nullptr;
+    const uint8_t* last_infl_base = nullptr;  // biased base of the inflated stream of the last decode
+    // coverm filter
+    unsigned long long* d_filter_anchor = nullptr;
+    uint8_t* d_filter_role = nullptr;
+    size_t filter_rec_cap = 0;
+    uint8_t* d_filter_out = nullptr;
+    size_t filter_out_cap = 0;
+    uint64_t filter_bytes = 0;
+    bool filter_planned = false;
     std::vector<void*> pinned;
     std::vector<cudaStream_t> streams;
     std::vector<cudaEvent_t> slot_events, done_events;
@@ -564,6 +574,7 @@ void cmb_destroy(cmb_ctx* c) {
     auto& d = c->dec;
     cudaFree(d.d_comp); cudaFree(d.d_inflated); cudaFree(d.d_coff); cudaFree(d.d_ustart); cudaFree(d.d_guess); cudaFree(d.d_exit);
     cudaFree(d.d_rec_base); cudaFree(d.d_cig_base); cudaFree(d.d_clen); cudaFree(d.d_isize); cudaFree(d.d_status); cudaFree(d.d_nrec);
+    cudaFree(d.d_filter_anchor); cudaFree(d.d_filter_role); cudaFree(d.d_filter_out);
     cudaFree(d.d_pair_key); cudaFree(d.d_pair_mate); cudaFree(d.d_pair_next); cudaFree(d.d_pair_tag); cudaFree(d.d_pair_head);
     cudaFree(d.d_ncig); cudaFree(d.d_dirty); cudaFree(d.d_tickets); cudaFree(d.d_t1_scratch); cudaFree(d.d_block_window); if (d.h_ones) cudaFreeHost(d.h_ones); cudaFree(d.d_cnt); cudaFree(d.d_rec_off); cudaFree(d.d_tuple_slab);
     for (auto p : d.pinned) cudaFreeHost(p);
@@ -1063,10 +1074,12 @@ int inflate_kind() {  // CMB_INFLATE: t1 (default) | g8 | w1
   }();
   return which;
 }
-// t1 only: one launch per copied window, stream-ordered behind the window's copy (no device-side waiting for data).
-// CMB_INFLATE_PERSISTENT=1 selects the single persistent launch whose threads poll the windows' arrival flags instead.
+// Default: ONE persistent launch whose threads poll the windows' arrival flags (bounded wait), so that every SM has work as soon
+// as the first window is in.  CMB_INFLATE_WINDOWS=1 (t1 only) launches per copied window instead, stream-ordered behind the
+// window's copy -- nothing on the device then waits for data, which tools that serialise streams (ncu, compute-sanitizer)
+// need; with the default 8 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS) those launches overlap poorly, hence not the default.
 bool inflate_per_window() {
-  static const bool v = inflate_kind() == 0 && !(getenv("CMB_INFLATE_PERSISTENT") && getenv("CMB_INFLATE_PERSISTENT")[0] == '1');
+  static const bool v = inflate_kind() == 0 && getenv("CMB_INFLATE_WINDOWS") && getenv("CMB_INFLATE_WINDOWS")[0] == '1';
   return v;
 }
 int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first_pass = true) {
@@ -1075,7 +1088,7 @@ int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first
   const uint32_t nb = a.b1 - a.b0;
   if (k == 0) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
-    const uint32_t grid = std::min<uint32_t>((nb + T1_THREADS - 1) / T1_THREADS, (uint32_t)c->sm_count * 4);
+    const uint32_t grid = std::min<uint32_t>((nb + T1_THREADS - 1) / T1_THREADS, (uint32_t)c->sm_count * 5);
     kd_inflate_t1<<<grid, T1_THREADS, T1_SMEM_BYTES, st>>>(a);
     CU_TRY(c, cudaGetLastError());
     kd_crc32<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)c->sm_count * 8), 256, 0, st>>>(a);
@@ -1107,7 +1120,7 @@ int dec_grow(cmb_ctx* c, T*& p, size_t& cap, size_t need, size_t extra_bytes = 0
 }  // namespace
 
 namespace {
-int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out);
+int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out, bool decode_only);
 }
 // Device memory for the decode buffers (compressed file + inflated stream + tuples) is requested before anything is
 // accumulated, so running out of it simply declines the sample: the host decoder needs only the staging batches.
@@ -1120,9 +1133,91 @@ extern "C" int cmb_last_bgzf_batch(cmb_ctx* c, cmb_read_batch* dev_batch, uint32
   return CMB_OK;
 }
 
-extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) {
-  if (c) c->dec.last_valid = false;
-  const int rc = submit_bgzf_impl(c, in, out);
+namespace {
+int bgzf_entry(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out, bool decode_only);
+}
+extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) { return bgzf_entry(c, in, out, false); }
+extern "C" int cmb_decode_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) { return bgzf_entry(c, in, out, true); }
+
+extern "C" int cmb_filter_plan(cmb_ctx* c, int inverse, uint64_t* n_records, uint64_t* n_bytes) {
+  if (!c || !n_records || !n_bytes) return fail(c, CMB_E_ARG, "cmb_filter_plan: null argument");
+  auto& d = c->dec;
+  if (!d.last_valid || !d.d_tuple_slab || !c->have_params) return fail(c, CMB_E_ARG, "cmb_filter_plan: no device-decoded sample is resident (cmb_decode_bgzf first)");
+  CU_TRY(c, cudaSetDevice(c->device));
+  *n_records = 0;
+  *n_bytes = 0;
+  d.filter_planned = false;
+  const uint32_t n = d.last_n_rec;
+  if (n == 0) {
+    d.filter_bytes = 0;
+    d.filter_planned = true;
+    return CMB_OK;
+  }
+  const bool pair_path = !(c->mode.filter_single_reads && !c->mode.filter_pairs);
+  if (pair_path && !d.last_mate) return fail(c, CMB_E_ARG, "cmb_filter_plan: the sample was decoded without mate matching (set the parameters before cmb_decode_bgzf)");
+  if (d.filter_rec_cap < (size_t)n + 1 || !d.d_filter_anchor) {
+    cudaFree(d.d_filter_anchor); cudaFree(d.d_filter_role);
+    d.d_filter_anchor = nullptr; d.d_filter_role = nullptr; d.filter_rec_cap = 0;
+    const size_t want = (size_t)n + n / 8 + 16;
+    CU_TRY(c, cudaMalloc(&d.d_filter_anchor, 8 * want));
+    CU_TRY(c, cudaMalloc(&d.d_filter_role, want));
+    d.filter_rec_cap = want;
+  }
+  cmb_read_batch tb;
+  carve_batch(d.d_tuple_slab, d.last_n_rec, d.last_n_cig, &tb);
+  FilterArgs a{};
+  a.data = d.last_infl_base; a.rec_off = d.d_rec_off; a.n = n; a.flag = tb.flag; a.mapq = tb.mapq; a.nm_state = tb.nm_state; a.nm = tb.nm;
+  a.l_seq = tb.l_seq; a.aligned = tb.aligned; a.del = tb.del; a.mate = pair_path ? d.last_mate : nullptr; a.p = c->params;
+  a.filter_single = c->mode.filter_single_reads; a.pair_path = pair_path; a.filter_out = inverse ? 0 : 1;
+  a.anchor_bytes = d.d_filter_anchor; a.role = d.d_filter_role; a.error_flags = d.d_cnt + 12; a.n_emit = (unsigned long long*)(d.d_cnt + 14);
+  CU_TRY(c, cudaMemsetAsync(d.d_cnt + 12, 0, 16, c->stream));
+  kf_decide<<<(n + 255) / 256, 256, 0, c->stream>>>(a);
+  kf_scan<<<1, 1024, 0, c->stream>>>(d.d_filter_anchor, n);
+  CU_TRY(c, cudaGetLastError());
+  uint32_t h[4];
+  unsigned long long total = 0;
+  CU_TRY(c, cudaMemcpyAsync(h, d.d_cnt + 12, 16, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaMemcpyAsync(&total, d.d_filter_anchor + n, 8, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  if (h[0] & ERR_NM)
+    return fail(c, CMB_E_NM, "Mapping record encountered that does not have an 'NM' auxiliary tag in the SAM/BAM format. This is required to work out some coverage statistics");
+  unsigned long long n_emit;
+  memcpy(&n_emit, h + 2, 8);
+  if (d.filter_out_cap < total || !d.d_filter_out) {
+    cudaFree(d.d_filter_out);
+    d.d_filter_out = nullptr;
+    d.filter_out_cap = 0;
+    const size_t want = (size_t)total + (size_t)total / 8 + 4096;
+    CU_TRY(c, cudaMalloc(&d.d_filter_out, want));
+    d.filter_out_cap = want;
+  }
+  a.out = d.d_filter_out;
+  kf_gather<<<(n + 7) / 8, 256, 0, c->stream>>>(a);
+  CU_TRY(c, cudaGetLastError());
+  d.filter_bytes = total;
+  d.filter_planned = true;
+  *n_records = n_emit;
+  *n_bytes = total;
+  return CMB_OK;
+}
+
+extern "C" int cmb_filter_fetch(cmb_ctx* c, uint8_t* records, uint64_t n_bytes) {
+  if (!c || (!records && n_bytes)) return fail(c, CMB_E_ARG, "cmb_filter_fetch: null argument");
+  auto& d = c->dec;
+  if (!d.filter_planned || n_bytes != d.filter_bytes) return fail(c, CMB_E_ARG, "cmb_filter_fetch: call cmb_filter_plan first and pass the size it reported");
+  CU_TRY(c, cudaSetDevice(c->device));
+  if (n_bytes) CU_TRY(c, cudaMemcpyAsync(records, d.d_filter_out, n_bytes, cudaMemcpyDeviceToHost, c->stream));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  return CMB_OK;
+}
+
+namespace {
+int bgzf_entry(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out, bool decode_only) {
+  if (c) {
+    c->dec.last_valid = false;
+    c->dec.filter_planned = false;
+  }
+  const int rc = submit_bgzf_impl(c, in, out, decode_only);
   if (rc == CMB_E_NOMEM) {
     cudaGetLastError();
     auto& d = c->dec;  // give the big buffers back so that the rest of the sample has room
@@ -1134,11 +1229,13 @@ extern "C" int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_re
   }
   return rc;
 }
+}  // namespace
 namespace {
-int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) {
+int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out, bool decode_only) {
   if (!c || !in || !out || !in->data || !in->block_coffset || !in->block_clen || !in->block_isize)
     return fail(c, CMB_E_ARG, "cmb_submit_bgzf: null argument");
-  if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: no sample in progress");
+  if (!decode_only && !c->in_sample) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: no sample in progress");
+  if (decode_only && (c->in_sample || !c->have_params)) return fail(c, CMB_E_ARG, "cmb_decode_bgzf: set the parameters first; not inside a sample");
   if (c->n_acquired) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: a staging batch is still acquired");
   *out = cmb_bgzf_result{};
   const uint32_t nb = in->n_blocks;
@@ -1575,9 +1672,14 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
     memcpy(&out->n_records, h_cnt + 10, 8);  // records this call owns (all of them unless ranged)
     d.last_valid = true;
     d.last_mate = nullptr;
-    if (c->mode.filter_pairs) {  // mate matching on the device (filter.rs:117-233; cmb_pairs.cuh)
+    d.last_infl_base = infl_base;
+    // mate matching on the device (filter.rs:117-233; cmb_pairs.cuh): for coverage when the pair thresholds apply; for
+    // `coverm filter` whenever the filter's pair path runs (everything but "single-read thresholds only", filter.rs:88)
+    const bool need_mates = decode_only ? !(c->mode.filter_single_reads && !c->mode.filter_pairs) : (bool)c->mode.filter_pairs;
+    if (need_mates) {
       if (d.pair_rec_cap < (size_t)n_rec || !d.d_pair_key) {
-        cudaFree(d.d_pair_key); cudaFree(d.d_pair_mate); cudaFree(d.d_pair_next);
+        cudaFree(d.d_filter_anchor); cudaFree(d.d_filter_role); cudaFree(d.d_filter_out);
+    cudaFree(d.d_pair_key); cudaFree(d.d_pair_mate); cudaFree(d.d_pair_next);
         d.d_pair_key = nullptr; d.d_pair_mate = nullptr; d.d_pair_next = nullptr; d.pair_rec_cap = 0;
         const size_t want = (size_t)n_rec + (size_t)n_rec / 8 + 16;
         CU_TRY(c, cudaMalloc(&d.d_pair_key, 8 * want));
@@ -1612,7 +1714,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out)
       d.last_mate = d.d_pair_mate;
     }
     CU_TRY(c, cudaEventRecord(d.ev[4], c->stream));
-    if (c->n_local) {
+    if (c->n_local && !decode_only) {
       // records that start before excl_end_block are this rank's exclusive share of the stream (cmb_kept_tid_range)
       uint32_t excl_n = 0xffffffffu;
       if (in->ranged && in->excl_end_block < walk_end) {

@@ -18,12 +18,14 @@
 #include <thread>
 
 #include "drivers.hpp"
+#include "filter_command.hpp"
 
 namespace cmbh {
 
 struct CliOptions {
   std::string sub;
-  std::vector<std::string> bam_files, methods;
+  std::vector<std::string> bam_files, methods, output_bam_files;
+  bool inverse = false;
   std::optional<uint32_t> min_read_aligned_length, min_read_aligned_length_pair;
   std::optional<float> min_read_percent_identity, min_read_aligned_percent, min_read_percent_identity_pair,
       min_read_aligned_percent_pair;
@@ -59,7 +61,8 @@ inline CliOptions parse_cli(const std::vector<std::string>& args) {
   CliOptions o;
   if (args.empty()) usage("a subcommand (contig | genome) is required");
   o.sub = args[0];
-  if (o.sub != "contig" && o.sub != "genome") usage("unrecognized subcommand '" + o.sub + "'");
+  const bool filter_sub = o.sub == "filter" || o.sub == "filter-names";
+  if (o.sub != "contig" && o.sub != "genome" && !filter_sub) usage("unrecognized subcommand '" + o.sub + "'");
   if (o.sub == "genome") {
     o.min_covered_fraction = 10.0f;  // cli.rs:2065
     o.methods = {"relative_abundance"};
@@ -82,6 +85,8 @@ inline CliOptions parse_cli(const std::vector<std::string>& args) {
       return args[++i];
     };
     if (a == "-b" || a == "--bam-files") list = &o.bam_files;
+    else if (filter_sub && (a == "-o" || a == "--output-bam-files")) list = &o.output_bam_files;
+    else if (filter_sub && a == "--inverse") o.inverse = true;
     else if (a == "-m" || a == "--methods" || a == "--method") {
       if (!methods_given) o.methods.clear();
       methods_given = true;
@@ -307,6 +312,55 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
   CliResult res;
   try {
     const CliOptions o = parse_cli(args);
+    if (o.sub == "filter" || o.sub == "filter-names") {  // coverm.rs:408-472
+      if (o.sub == "filter" && o.bam_files.size() != o.output_bam_files.size())
+        throw ExitError(1, "The number of input BAM files must be the same as the number output");
+      cmb_params fp{};  // FilterParameters::generate_from_clap (coverm.rs:1648-1678)
+      fp.include_improper_pairs = !o.proper_pairs_only;
+      fp.include_secondary = o.include_secondary;
+      fp.include_supplementary = !o.exclude_supplementary;
+      if (o.lib_flags) {
+        int i, s2, sec;
+        if (sscanf(o.lib_flags->c_str(), "%d,%d,%d", &i, &s2, &sec) != 3) usage("--lib-flags expects I,S,SEC");
+        fp.include_improper_pairs = i != 0;
+        fp.include_supplementary = s2 != 0;
+        fp.include_secondary = sec != 0;
+      }
+      fp.min_aligned_length_single = o.min_read_aligned_length.value_or(0);
+      fp.min_percent_identity_single = parse_percentage(o.min_read_percent_identity);
+      fp.min_aligned_percent_single = parse_percentage(o.min_read_aligned_percent);
+      fp.min_mapq = o.min_mapq.value_or(255);
+      fp.min_aligned_length_pair = o.min_read_aligned_length_pair.value_or(0);
+      fp.min_percent_identity_pair = parse_percentage(o.min_read_percent_identity_pair);
+      fp.min_aligned_percent_pair = parse_percentage(o.min_read_aligned_percent_pair);
+      fp.filtering = 1;  // the filter always runs; which of its two paths is decided by the thresholds (filter.rs:48-61)
+      std::unique_ptr<DeviceSession> own;
+      DeviceSession* session = shared_session;
+      if (!session) {
+        own = std::make_unique<DeviceSession>(o.device, o.threads);
+        session = own.get();
+      }
+      for (size_t k = 0; k < o.bam_files.size(); ++k) {
+        InputSpec in;
+        in.path = o.bam_files[k];
+        for (auto& m : memory_inputs)
+          if (m.path == in.path) in = m;
+        const FilterRun run = filter_one_input(*session, in, fp, o.inverse);
+        if (o.timing) err << "#filter\tsample=" << k << "\trecords_out=" << run.n_records << "\tdevice=" << (run.on_device ? 1 : 0) << '\n';
+        if (o.sub == "filter-names") {
+          for (size_t off = 0; off + 4 <= run.records.size(); off += 4 + (size_t)rd_u32(run.records.data() + off)) out << bam_qname(run.records.data() + off) << '\n';
+        } else {
+          std::ofstream bam(o.output_bam_files[k], std::ios::binary);
+          if (!bam) throw Panic("Failed to write BAM file " + o.output_bam_files[k]);
+          write_bgzf(bam, {run.header_bytes.data(), run.records.data()}, {run.header_bytes.size(), run.records.size()}, session->pool());
+          bam.flush();
+          if (!bam) throw Panic("Failed to write BAM record");
+        }
+      }
+      out.flush();
+      res.status = 0;
+      return res;
+    }
     Plan plan = make_plan(o);
     std::ofstream file;
     std::ostream* os = &out;

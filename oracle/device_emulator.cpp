@@ -463,6 +463,11 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
   return submit(c, b, (uint32_t)tid.size(), (uint32_t)out->n_intervals, excl_n == (size_t)-1 ? 0xffffffffu : (uint32_t)excl_n);
 }
 
+// `coverm filter` on the device is not emulated: the host's own filter loop (filter_command.hpp) is what the CPU tests check.
+int cmb_decode_bgzf(cmb_ctx* c, const cmb_bgzf_input*, cmb_bgzf_result*) { return fail(c, CMB_E_DECLINED, "emulator: no device-side filter"); }
+int cmb_filter_plan(cmb_ctx* c, int, uint64_t*, uint64_t*) { return fail(c, CMB_E_ARG, "emulator: no device-side filter"); }
+int cmb_filter_fetch(cmb_ctx* c, uint8_t*, uint64_t) { return fail(c, CMB_E_ARG, "emulator: no device-side filter"); }
+
 // No NCCL in the emulator: groups of emulated ranks exchange through the host all-gather callback of the session.
 int cmb_comm_unique_id(uint8_t*) { return fail(nullptr, CMB_E_ARG, "emulator: no NCCL"); }
 int cmb_comm_init(cmb_ctx* c, const uint8_t*, int, int) { return fail(c, CMB_E_ARG, "emulator: no NCCL"); }

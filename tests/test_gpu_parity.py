@@ -11,11 +11,11 @@ import pytest
 
 import coverm_b200
 from case_runner import DATA, ORACLE_BIN, check_case, run_case
-from reference_cases import CASES, CLI_CASES
+from reference_cases import CASES, CLI_CASES, FILTER_CASES
 
 pytestmark = pytest.mark.gpu
 
-GPU_CASES = [c for c in CASES + CLI_CASES if c["sub"] in ("contig", "genome")]
+GPU_CASES = [c for c in CASES + CLI_CASES + FILTER_CASES if c["sub"] in ("contig", "genome", "filter-names")]
 
 
 @pytest.mark.parametrize("case", GPU_CASES, ids=[f"{c['sub']}@{c['ref']}" for c in GPU_CASES])
@@ -247,3 +247,64 @@ def test_pair_filter_settings_of_the_reference_tests_on_the_device(bam, length, 
         argv += ["--min-read-aligned-percent-pair", str(percent)]
     g = _assert_same(argv + ["-b", os.path.join(DATA, bam)], env={"CMB_PIPELINE_STATS": "1"})
     assert any(l.startswith("#device_decode\tblocks=") for l in g.stderr.splitlines()), g.stderr[-800:]
+
+
+# ---------------------------------------------------------------------------------------------- coverm filter
+def _bam_records(path):
+    """(header bytes, [record bytes]) of a BAM file, via zlib."""
+    import struct
+    import zlib
+    raw = open(path, "rb").read()
+    data, o = bytearray(), 0
+    while o < len(raw):
+        bsize = struct.unpack_from("<H", raw, o + 16)[0] + 1
+        data += zlib.decompress(raw[o + 18:o + bsize - 8], -15)
+        o += bsize
+    l_text = struct.unpack_from("<I", data, 4)[0]
+    n_ref = struct.unpack_from("<I", data, 8 + l_text)[0]
+    p = 12 + l_text
+    for _ in range(n_ref):
+        p += 8 + struct.unpack_from("<I", data, p)[0]
+    header, recs = bytes(data[:p]), []
+    while p < len(data):
+        bs = struct.unpack_from("<I", data, p)[0]
+        recs.append(bytes(data[p:p + 4 + bs]))
+        p += 4 + bs
+    return header, recs
+
+
+FILTER_RUNS = [
+    ("small", ["--min-read-percent-identity", "97", "--min-read-aligned-length", "100"]),
+    ("small", ["--min-read-percent-identity", "97", "--inverse"]),
+    ("small", ["--proper-pairs-only", "--min-read-aligned-length-pair", "250", "--min-read-percent-identity-pair", "95"]),
+    ("small", ["--proper-pairs-only", "--min-read-aligned-length-pair", "280", "--inverse"]),
+    ("small", ["--min-mapq", "30"]),
+    ("deep", ["--proper-pairs-only", "--min-mapq", "20", "--min-read-aligned-percent", "95", "--exclude-supplementary"]),
+    ("mags", []),
+]
+
+
+@pytest.mark.parametrize("which,extra", FILTER_RUNS, ids=[f"{w}:{' '.join(e)}#{i}" for i, (w, e) in enumerate(FILTER_RUNS)])
+def test_coverm_filter_on_the_device(synth, tmp_path, which, extra):
+    """`coverm filter` (coverm.rs:408-472): the records the device returns, in its order, are exactly the records the oracle's
+    ReferenceSortedBamFilter returns (same names in the same order, byte-identical records, the input's header) -- and the
+    host's own filter loop (CMB_HOST_DECODE=1) writes the same file content."""
+    outs = []
+    for env in ({}, {"CMB_HOST_DECODE": "1"}):
+        out = str(tmp_path / f"out{len(outs)}.bam")
+        p = subprocess.run([coverm_b200.COVERM_BIN, "filter", "-b", synth[which], "-o", out, "-t", "8", "--timing"] + extra, capture_output=True, text=True,
+                           timeout=900, env=dict(os.environ, **env))
+        assert p.returncode == 0, p.stderr[-800:]
+        assert ("device=1" in p.stderr) == (not env), p.stderr[-300:]
+        outs.append(_bam_records(out))
+    names = subprocess.run([ORACLE_BIN, "filter-names", "-b", synth[which]] + extra, capture_output=True, text=True, timeout=900)
+    assert names.returncode == 0, names.stderr[-500:]
+    want = names.stdout.split("\n")[:-1]
+    in_header, in_recs = _bam_records(synth[which])
+    for header, recs in outs:
+        assert header == in_header
+        got = [r[36:36 + r[12] - 1].decode() for r in recs]
+        assert got == want
+    assert outs[0][1] == outs[1][1]
+    by_bytes = set(in_recs)
+    assert all(r in by_bytes for r in outs[0][1][:2000])

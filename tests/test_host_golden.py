@@ -11,7 +11,9 @@ from case_runner import ROOT, check_case, run_case
 from reference_cases import CASES, CLI_CASES
 
 HOSTCHECK = os.path.join(ROOT, "oracle", "coverm_hostcheck")
-HOST_CASES = [c for c in CASES + CLI_CASES if c["sub"] in ("contig", "genome")]
+from reference_cases import FILTER_CASES  # noqa: E402
+
+HOST_CASES = [c for c in CASES + CLI_CASES + FILTER_CASES if c["sub"] in ("contig", "genome", "filter-names")]
 
 
 @pytest.fixture(scope="session", autouse=True)
@@ -67,3 +69,44 @@ def test_in_memory_sink_bulk_path_through_the_c_abi():
 @pytest.mark.parametrize("case", HOST_CASES, ids=[f"{c['sub']}@{c['ref']}" for c in HOST_CASES])
 def test_device_decode_branch_matches_reference_golden(case):
     check_case(case, run_case(HOSTCHECK, case, extra_args=["-t", "2"], env={"CMB_EMU_BGZF": "1"}))
+
+
+def test_coverm_filter_writes_the_filtered_bam(tmp_path):
+    """`coverm filter` through the host's filter loop (no GPU): output header == input header, records == the oracle's
+    filter-names sequence, byte-identical to the input's records, file readable as BGZF with an EOF marker."""
+    import struct
+    import zlib
+    from case_runner import DATA, ORACLE_BIN
+
+    def records(path):
+        raw = open(path, "rb").read()
+        assert raw.endswith(bytes.fromhex("1f8b08040000000000ff0600424302001b0003000000000000000000"))
+        data, o = bytearray(), 0
+        while o < len(raw):
+            bsize = struct.unpack_from("<H", raw, o + 16)[0] + 1
+            data += zlib.decompress(raw[o + 18:o + bsize - 8], -15)
+            o += bsize
+        l_text = struct.unpack_from("<I", data, 4)[0]
+        n_ref = struct.unpack_from("<I", data, 8 + l_text)[0]
+        p = 12 + l_text
+        for _ in range(n_ref):
+            p += 8 + struct.unpack_from("<I", data, p)[0]
+        header, recs = bytes(data[:p]), []
+        while p < len(data):
+            bs = struct.unpack_from("<I", data, p)[0]
+            recs.append(bytes(data[p:p + 4 + bs]))
+            p += 4 + bs
+        return header, recs
+
+    src = os.path.join(DATA, "1.bam")
+    for extra in (["--min-read-percent-identity", "95"], ["--proper-pairs-only", "--min-read-aligned-length-pair", "150"],
+                  ["--proper-pairs-only", "--min-read-aligned-length-pair", "150", "--inverse"], []):
+        out = str(tmp_path / "f.bam")
+        p = subprocess.run([HOSTCHECK, "filter", "-b", src, "-o", out, "-t", "3"] + extra, capture_output=True, text=True)
+        assert p.returncode == 0, p.stderr[-500:]
+        want = subprocess.run([ORACLE_BIN, "filter-names", "-b", src] + extra, capture_output=True, text=True, check=True).stdout.split("\n")[:-1]
+        in_header, in_recs = records(src)
+        header, recs = records(out)
+        assert header == in_header
+        assert [r[36:36 + r[12] - 1].decode() for r in recs] == want
+        assert set(recs) <= set(in_recs)
