@@ -197,6 +197,7 @@ struct cmb_ctx {
     uint32_t* d_pair_head = nullptr;
     size_t pair_table_cap = 0;
     const int32_t* last_mate = nullptr;
+    uint32_t last_excl_n = 0xffffffffu;
     const uint8_t* last_infl_base = nullptr;  // biased base of the inflated stream of the last decode
     // coverm filter
     unsigned long long* d_filter_anchor = nullptr;
@@ -699,6 +700,10 @@ int cmb_set_reference(cmb_ctx* c, uint32_t n_contigs, const uint64_t* contig_len
   // histogram record buffers: one 8 B record per 8 arena elements is far above anything a real sample produces
   c->rec_capacity = (uint32_t)std::min<uint64_t>(0xfffffff0ull, std::max<uint64_t>(1u << 20, c->arena_elems / 8));
   c->ovf_capacity = (uint32_t)std::min<uint64_t>(1u << 26, std::max<uint64_t>(1u << 20, c->arena_elems / 64));
+  if (getenv("CMB_TEST_SMALL_HIST")) {  // testing aid: buffers that overflow at once (cmb_grow_buffers path)
+    c->rec_capacity = 256;
+    c->ovf_capacity = 64;
+  }
   CU_TRY(c, cudaMalloc(&c->d_rec, 8ull * c->rec_capacity));
   CU_TRY(c, cudaMalloc(&c->d_warp_table, 8ull * c->n_chunks * HIST_SLOTS));
   CU_TRY(c, cudaMalloc(&c->d_ovf, 16ull * c->ovf_capacity));
@@ -756,7 +761,8 @@ int cmb_begin_sample(cmb_ctx* c) {
   CU_TRY(c, cudaEventRecord(c->ev[1], c->stream));
   c->arena_dirty = true;  // until K2 has cleaned it
   if ((c->params.want & CMB_WANT_HIST_CSR) && c->n_local) {
-    const uint64_t want = std::max<uint64_t>(1u << 20, c->arena_elems / 16);
+    uint64_t want = std::max<uint64_t>(1u << 20, c->arena_elems / 16);
+    if (getenv("CMB_TEST_SMALL_HIST")) want = 64;  // testing aid: start with buffers that overflow at once (cmb_grow_buffers path)
     if (c->pair_capacity < want) {
       cudaFree(c->d_pairs);
       c->d_pairs = nullptr;
@@ -827,9 +833,9 @@ int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* dev, uint32_t n_re
   if (c->n_local == 0) return CMB_OK;
   CU_TRY(c, cudaSetDevice(c->device));
   // re-submitting the tuples of the last device decode (cmb_last_bgzf_batch) in pair mode: its mate table goes with it
-  const int32_t* mate = (c->dec.last_valid && c->dec.last_mate && (const void*)dev->tid == c->dec.d_tuple_slab && c->mode.filter_pairs)
-                            ? c->dec.last_mate : nullptr;
-  return launch_k1(c, *dev, n_records, n_intervals, 0xffffffffu, mate);
+  const bool is_last = c->dec.last_valid && (const void*)dev->tid == c->dec.d_tuple_slab;
+  const int32_t* mate = (is_last && c->dec.last_mate && c->mode.filter_pairs) ? c->dec.last_mate : nullptr;
+  return launch_k1(c, *dev, n_records, n_intervals, is_last ? c->dec.last_excl_n : 0xffffffffu, mate);
 }
 
 int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** dev_stats) {
@@ -883,6 +889,34 @@ int cmb_fetch_pairs(cmb_ctx* c, cmb_hist_pair* pairs, uint64_t n_pairs) {
     CU_TRY(c, cudaMemcpyAsync(pairs, c->d_pairs, sizeof(cmb_hist_pair) * n_pairs, cudaMemcpyDeviceToHost, c->stream));
     CU_TRY(c, cudaStreamSynchronize(c->stream));
   }
+  return CMB_OK;
+}
+
+int cmb_grow_buffers(cmb_ctx* c) {
+  if (!c || !c->d_rows) return fail(c, CMB_E_ARG, "cmb_grow_buffers: no reference set");
+  if (c->in_sample) return fail(c, CMB_E_ARG, "cmb_grow_buffers: a sample is in progress");
+  if (c->n_local == 0) return CMB_OK;
+  CU_TRY(c, cudaSetDevice(c->device));
+  CU_TRY(c, cudaStreamSynchronize(c->stream));
+  const uint64_t rec = std::min<uint64_t>(0xfffffff0ull, (uint64_t)c->rec_capacity * 4);
+  const uint64_t ovf = std::min<uint64_t>(1ull << 30, (uint64_t)c->ovf_capacity * 4);
+  cudaFree(c->d_rec);
+  cudaFree(c->d_ovf);
+  c->d_rec = nullptr;
+  c->d_ovf = nullptr;
+  CU_TRY(c, cudaMalloc(&c->d_rec, 8ull * rec));
+  CU_TRY(c, cudaMalloc(&c->d_ovf, 16ull * ovf));
+  c->rec_capacity = (uint32_t)rec;
+  c->ovf_capacity = (uint32_t)ovf;
+  if (c->d_pairs) {
+    const uint64_t want = c->pair_capacity * 4;
+    cudaFree(c->d_pairs);
+    c->d_pairs = nullptr;
+    c->pair_capacity = 0;
+    CU_TRY(c, cudaMalloc(&c->d_pairs, sizeof(cmb_hist_pair) * want));
+    c->pair_capacity = want;
+  }
+  c->arena_dirty = true;
   return CMB_OK;
 }
 
@@ -1518,6 +1552,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
       std::vector<uint32_t> again;
       for (uint32_t b = first_block; b < data_end; ++b)
         if (status[b] != INF_OK) again.push_back(b);
+      out->n_blocks_second_pass = (uint32_t)again.size();
       if (!again.empty()) {
         uint32_t* d_list = d.d_dirty;  // free until the record chain starts (nb entries)
         CU_TRY(c, cudaMemcpyAsync(d_list, again.data(), 4ull * again.size(), cudaMemcpyHostToDevice, c->stream));
@@ -1726,6 +1761,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
           excl_n = (uint32_t)base;
         }
       }
+      d.last_excl_n = excl_n;
       rc = launch_k1(c, tb, (uint32_t)n_rec, (uint32_t)n_cig, excl_n, d.last_mate);
       if (rc) return rc;
     }

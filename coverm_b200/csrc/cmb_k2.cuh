@@ -125,6 +125,37 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
     const uint32_t span = chunk * CHUNK_SPANS + t;
     int total = 0;
     uint32_t ev = 0;
+#if CMB_K2_COOP && CMB_SPAN == 32
+    {
+      // Deltas are sparse (under 1 % of the positions; about three spans in four hold none), but a branch per thread saves
+      // nothing in SIMT -- some lane of the warp always has events.  So the work is compacted across the warp: every lane only
+      // ORs its 32 values together (a span is one 128-byte tile row); then the WARP visits each non-empty span of its lanes
+      // once, lane e taking element e of that row: one conflict-free LDS.32, one ballot (the non-zero mask) and one REDUX (the
+      // span total) replace the owner's thirty-two compares and adds, and the re-zeroing stores go out from the lanes that
+      // saw the events.
+      uint32_t any = 0;
+#pragma unroll
+      for (uint32_t j = 0; j < UNITS; ++j) {
+        const int4 q = *reinterpret_cast<const int4*>(rowp + ((j ^ (row & 7)) << 4));  // every unit once, bank-conflict-free
+        any |= (uint32_t)((q.x | q.y) | (q.z | q.w));
+      }
+      uint32_t busy = __ballot_sync(FULL, any != 0);
+      const uint8_t* tile = smem + s * CHUNK_BYTES;
+      while (busy) {
+        const uint32_t src = (uint32_t)__ffs(busy) - 1;
+        busy &= busy - 1;
+        const uint32_t r2 = (t & ~31u) + src;  // tile row == span of lane `src`
+        const int v = *reinterpret_cast<const int*>(tile + r2 * 128 + (((lane >> 2) ^ (r2 & 7)) << 4) + ((lane & 3) << 2));
+        const uint32_t m = __ballot_sync(FULL, v != 0);
+        const int sum = __reduce_add_sync(FULL, v);
+        if (lane == src) {
+          total = sum;
+          ev = m;
+        }
+        if (CLEAN && v != 0) a.arena[((uint64_t)chunk * CHUNK_SPANS + r2) * SPAN + lane] = 0;
+      }
+    }
+#else
     {
       int4* g = reinterpret_cast<int4*>(a.arena + (uint64_t)span * SPAN);
 #pragma unroll
@@ -137,6 +168,7 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
         if (CLEAN && e4) g[j] = make_int4(0, 0, 0, 0);  // re-zero only the 16 B units that hold an event
       }
     }
+#endif
 
     // ---- which contig owns this span
     const uint32_t cf = __ldg(a.chunk_first + chunk);

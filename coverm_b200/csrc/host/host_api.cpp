@@ -167,6 +167,7 @@ int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_
     si.range_probes = t.range_probes;
     si.tid_begin = t.tid_begin;
     si.tid_end = t.tid_end;
+    si.decode_second_pass_blocks = t.bgzf.n_blocks_second_pass;
     si.gather_s = t.gather_s;
   }
   return 0;

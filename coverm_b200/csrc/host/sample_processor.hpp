@@ -721,13 +721,29 @@ class DeviceSession {
     ensure_rows(n_rows);
     res.rows = rows_buf_;
     uint64_t n_pairs = 0;
+    // A histogram buffer of the device overflowed (very deep coverage over many small contigs): with the sample's tuples still in
+    // device memory the buffers are enlarged and the kernels run again; otherwise the error stands.
+    auto end_sample = [&](cmb_contig_stats* rows_out) {
+      int r2 = cmb_end_sample(ctx_, rows_out, nullptr, 0, &n_pairs);
+      for (int attempt = 0; r2 == CMB_E_CAPACITY && decoded_on_device && attempt < 4; ++attempt) {
+        cmb_read_batch again{};
+        uint32_t nr = 0, ni = 0;
+        if (cmb_last_bgzf_batch(ctx_, &again, &nr, &ni) != CMB_OK) break;
+        if (getenv("CMB_PIPELINE_STATS")) fprintf(stderr, "#capacity_retry\tattempt=%d\n", attempt + 1);
+        if ((r2 = cmb_grow_buffers(ctx_)) != CMB_OK) break;
+        if ((r2 = cmb_begin_sample(ctx_)) != CMB_OK) break;
+        if ((r2 = cmb_submit_device_batch(ctx_, &again, nr, ni)) != CMB_OK) break;
+        r2 = cmb_end_sample(ctx_, rows_out, nullptr, 0, &n_pairs);
+      }
+      return r2;
+    };
     if (shard && group_nccl_) {
       // rows (and pairs) stay on the device: cmb_allgather_stats completes the table there and copies it back once
-      rc = cmb_end_sample(ctx_, nullptr, nullptr, 0, &n_pairs);
+      rc = end_sample(nullptr);
       if (rc) throw_device_error(ctx_, rc);
       shard->n_pairs = n_pairs;
     } else {
-      rc = cmb_end_sample(ctx_, rows_buf_, nullptr, 0, &n_pairs);
+      rc = end_sample(rows_buf_);
       if (rc) throw_device_error(ctx_, rc);
       if ((params.want & CMB_WANT_HIST_CSR) && n_pairs) {
         res.pairs.resize(n_pairs);

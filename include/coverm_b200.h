@@ -260,7 +260,8 @@ typedef struct cmb_bgzf_result {
   uint32_t chain_repairs;         /* record-chain repair rounds                                        */
   float ms_copy_inflate, ms_chain, ms_extract, ms_total; /* CUDA events on the ctx stream              */
   uint32_t n_launches;            /* decode kernels launched (inflate windows + chain + extract)       */
-  uint32_t reserved;
+  uint32_t n_blocks_second_pass;  /* blocks the first inflate pass declined (incl. windows that did not arrive within the bounded
+                                     wait, status 31) and the one-stream-per-warp kernel took over      */
   uint64_t h2d_bytes;             /* compressed bytes + block table copied host->device                */
 } cmb_bgzf_result;
 int cmb_submit_bgzf(cmb_ctx* ctx, const cmb_bgzf_input* in, cmb_bgzf_result* out);
@@ -280,6 +281,11 @@ int cmb_filter_fetch(cmb_ctx* ctx, uint8_t* records, uint64_t n_bytes);
  * cmb_submit_bgzf / cmb_destroy): DEVICE pointers laid out as cmb_read_batch, ready for cmb_submit_device_batch.
  * Lets a caller re-run the filter/scan/reduce kernels over an already decoded sample (device-only timing, parameter sweeps). */
 int cmb_last_bgzf_batch(cmb_ctx* ctx, cmb_read_batch* dev_batch, uint32_t* n_records, uint32_t* n_intervals);
+
+/* After cmb_end_sample* failed with CMB_E_CAPACITY (a device-side histogram buffer overflowed: very deep coverage over many
+ * small contigs): enlarges those buffers (x4).  A caller whose tuples are still in device memory (cmb_last_bgzf_batch) can then
+ * run the sample again -- cmb_begin_sample, cmb_submit_device_batch, cmb_end_sample. */
+int cmb_grow_buffers(cmb_ctx* ctx);
 
 /* Page-locked host memory for result buffers (cmb_end_sample copies straight into it at PCIe speed).  Plain malloc
  * semantics otherwise; free with cmb_host_free. */

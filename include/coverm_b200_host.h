@@ -45,7 +45,7 @@ typedef struct cmbh_sample_info {
   uint32_t shard_blocks, total_blocks; /* BGZF blocks this rank walked / blocks in the file */
   uint32_t range_probes;     /* blocks inflated on the host to find the rank's block range */
   uint32_t tid_begin, tid_end; /* contigs this rank owned for the sample */
-  uint32_t reserved;
+  uint32_t decode_second_pass_blocks; /* blocks the first device inflate pass declined or timed out on */
   double gather_s;           /* summary exchange + table gather (wall clock) */
 } cmbh_sample_info;
 

@@ -463,6 +463,7 @@ int cmb_submit_bgzf(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out) 
   return submit(c, b, (uint32_t)tid.size(), (uint32_t)out->n_intervals, excl_n == (size_t)-1 ? 0xffffffffu : (uint32_t)excl_n);
 }
 
+int cmb_grow_buffers(cmb_ctx*) { return CMB_OK; }
 // `coverm filter` on the device is not emulated: the host's own filter loop (filter_command.hpp) is what the CPU tests check.
 int cmb_decode_bgzf(cmb_ctx* c, const cmb_bgzf_input*, cmb_bgzf_result*) { return fail(c, CMB_E_DECLINED, "emulator: no device-side filter"); }
 int cmb_filter_plan(cmb_ctx* c, int, uint64_t*, uint64_t*) { return fail(c, CMB_E_ARG, "emulator: no device-side filter"); }

@@ -308,3 +308,11 @@ def test_coverm_filter_on_the_device(synth, tmp_path, which, extra):
     assert outs[0][1] == outs[1][1]
     by_bytes = set(in_recs)
     assert all(r in by_bytes for r in outs[0][1][:2000])
+
+
+def test_histogram_buffer_overflow_grows_and_retries(synth):
+    """CMB_TEST_SMALL_HIST starts the device's histogram record / overflow / pair buffers tiny: the first attempt overflows
+    (CMB_E_CAPACITY), the library enlarges them (cmb_grow_buffers) and the kernels run again over the tuples still in HBM."""
+    for argv in (["contig", "-m", "mean", "trimmed_mean", "variance", "-b", synth["deep"]], ["contig", "-m", "coverage_histogram", "-b", synth["small"]]):
+        g = _assert_same(argv, env={"CMB_TEST_SMALL_HIST": "1", "CMB_PIPELINE_STATS": "1"})
+        assert "#capacity_retry" in g.stderr, g.stderr[-600:]
