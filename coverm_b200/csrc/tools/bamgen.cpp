@@ -6,7 +6,7 @@
 //
 //   bamgen --out x.bam --contigs N --reads R [--median-len 4000 --sigma 0.8 --min-len 1000 --max-len 2000000]
 //          [--genomes G (names magNNNN~ctgNNNNN, definition TSV via --definition-out)] [--seed S] [--threads T]
-//          [--read-len 150] [--plain-fraction 0.88]
+//          [--read-len 150] [--contig-table names_and_lengths.tsv]
 #include <zlib.h>
 
 #include <algorithm>
@@ -52,7 +52,7 @@ struct Rng {  // splitmix64
 };
 
 struct Args {
-  std::string out, definition_out;
+  std::string out, definition_out, contig_table;
   uint64_t contigs = 1000, reads = 100000, seed = 1;
   double median_len = 4000, sigma = 0.8;
   uint64_t min_len = 1000, max_len = 2000000;
@@ -194,6 +194,7 @@ int main(int argc, char** argv) {
     if (s == "--out") a.out = val();
     else if (s == "--definition-out") a.definition_out = val();
     else if (s == "--contigs") a.contigs = strtoull(val(), nullptr, 10);
+    else if (s == "--contig-table") a.contig_table = val();  // "name<TAB>length" lines: use these reference sequences
     else if (s == "--reads") a.reads = strtoull(val(), nullptr, 10);
     else if (s == "--seed") a.seed = strtoull(val(), nullptr, 10);
     else if (s == "--median-len") a.median_len = atof(val());
@@ -216,6 +217,24 @@ int main(int argc, char** argv) {
   const uint32_t RL = std::max<uint32_t>(80, a.read_len);
 
   // ---- reference
+  std::vector<std::pair<std::string, uint32_t>> table;
+  if (!a.contig_table.empty()) {
+    FILE* tf = fopen(a.contig_table.c_str(), "r");
+    if (!tf) {
+      fprintf(stderr, "bamgen: cannot read %s\n", a.contig_table.c_str());
+      return 2;
+    }
+    char line[4096];
+    while (fgets(line, sizeof line, tf)) {
+      char* tab = strchr(line, '\t');
+      if (!tab) continue;
+      *tab = 0;
+      table.emplace_back(line, (uint32_t)strtoul(tab + 1, nullptr, 10));
+    }
+    fclose(tf);
+    a.contigs = table.size();
+    a.genomes = 0;
+  }
   Rng rr(a.seed * 0x9E3779B97F4A7C15ull + 17);
   std::vector<uint32_t> len(a.contigs);
   std::vector<std::string> names(a.contigs);
@@ -244,6 +263,10 @@ int main(int argc, char** argv) {
         snprintf(buf, sizeof buf, "c%07llu", (unsigned long long)c);
       }
       names[c] = buf;
+      if (!table.empty()) {
+        names[c] = table[c].first;
+        len[c] = std::max<uint32_t>(1, table[c].second);
+      }
     }
     // abundance is per genome (or per contig when there are no genomes): log-normal sigma 1.5
     std::vector<double> gab(a.genomes ? a.genomes : 0);
