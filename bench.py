@@ -400,7 +400,8 @@ def main():
         breakdown.append(res.samples[0])
     log("e2e step walls (s): " + " ".join(f"{w:.4f}" for w in step_walls))
     log("e2e per step: copy+inflate ms " + " ".join(f"{b['decode_copy_inflate_ms']:.1f}" for b in breakdown) + " | second-pass blocks " +
-        " ".join(str(b["decode_second_pass_blocks"]) for b in breakdown) + " | host blocks " + " ".join(str(b["decode_host_blocks"]) for b in breakdown))
+        " ".join(str(b["decode_second_pass_blocks"]) for b in breakdown) + " | host blocks " + " ".join(str(b["decode_host_blocks"]) for b in breakdown) + " | copy-enqueue wall ms " +
+        " ".join(f"{b['decode_copy_enqueue_wall_ms']:.0f}" for b in breakdown) + " | submit_bgzf host wall ms " + " ".join(f"{b['decode_host_wall_ms']:.0f}" for b in breakdown))
     log("e2e last step host timing: " + " | ".join(l for l in res.err.splitlines() if l.startswith("#timing")))
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t_e) / e2e_steps

@@ -81,7 +81,7 @@ class SampleInfo(C.Structure):
                 ("decode_host_blocks", C.c_uint32), ("decode_copy_inflate_ms", C.c_float), ("decode_chain_ms", C.c_float),
                 ("decode_extract_ms", C.c_float), ("decode_launches", C.c_uint32), ("group_ranks", C.c_uint32),
                 ("shard_blocks", C.c_uint32), ("total_blocks", C.c_uint32), ("range_probes", C.c_uint32), ("tid_begin", C.c_uint32), ("tid_end", C.c_uint32), ("decode_second_pass_blocks", C.c_uint32),
-                ("gather_s", C.c_double)]
+                ("gather_s", C.c_double), ("decode_copy_enqueue_wall_ms", C.c_float), ("decode_host_wall_ms", C.c_float)]
 
 
 class HostResult(C.Structure):

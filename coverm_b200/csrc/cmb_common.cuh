@@ -18,7 +18,7 @@ constexpr uint32_t CHUNK_ROWS = CHUNK / ROW_ELEMS;  // 256
 constexpr uint32_t K2_STAGES = CMB_K2_STAGES;
 constexpr uint32_t K2_WARPS = K2_THREADS / 32;  // 16
 #ifndef CMB_K2_COOP
-#define CMB_K2_COOP 1  // K2: warp-cooperative handling of the (sparse) non-empty spans; 0 = every thread scans its own 32 values
+#define CMB_K2_COOP 0  // K2 experiment: warp-cooperative handling of the non-empty spans (measured SLOWER: 2.85 vs 2.66 ms on config 2)
 #endif
 #ifndef CMB_HIST_SLOTS
 #define CMB_HIST_SLOTS 8

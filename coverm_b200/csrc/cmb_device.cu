@@ -1251,7 +1251,9 @@ int bgzf_entry(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out, bool 
     c->dec.last_valid = false;
     c->dec.filter_planned = false;
   }
+  const auto t_call0 = std::chrono::steady_clock::now();
   const int rc = submit_bgzf_impl(c, in, out, decode_only);
+  if (out) out->ms_host_wall = (float)std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_call0).count();
   if (rc == CMB_E_NOMEM) {
     cudaGetLastError();
     auto& d = c->dec;  // give the big buffers back so that the rest of the sample has room
@@ -1492,7 +1494,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     for (auto& th : threads) th.join();
   }
   const double copy_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - copy_t0).count();
-  (void)copy_wall_ms;
+  out->ms_copy_enqueue_wall = (float)copy_wall_ms;
   if (first_err.load()) {  // release the warps still waiting for windows that will never arrive
     cudaMemsetAsync(d.d_tickets + 1, 1, 4 * windows.size(), d.streams[0]);
     cudaStreamSynchronize(d.streams[0]);

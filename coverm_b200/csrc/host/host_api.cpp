@@ -169,6 +169,8 @@ int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_
     si.tid_end = t.tid_end;
     si.decode_second_pass_blocks = t.bgzf.n_blocks_second_pass;
     si.gather_s = t.gather_s;
+    si.decode_copy_enqueue_wall_ms = t.bgzf.ms_copy_enqueue_wall;
+    si.decode_host_wall_ms = t.bgzf.ms_host_wall;
   }
   return 0;
 }

@@ -263,6 +263,8 @@ typedef struct cmb_bgzf_result {
   uint32_t n_blocks_second_pass;  /* blocks the first inflate pass declined (incl. windows that did not arrive within the bounded
                                      wait, status 31) and the one-stream-per-warp kernel took over      */
   uint64_t h2d_bytes;             /* compressed bytes + block table copied host->device                */
+  float ms_copy_enqueue_wall;     /* host wall clock spent enqueueing the window copies (diagnostics)  */
+  float ms_host_wall;             /* host wall clock of the whole call                                  */
 } cmb_bgzf_result;
 int cmb_submit_bgzf(cmb_ctx* ctx, const cmb_bgzf_input* in, cmb_bgzf_result* out);
 /* ---- `coverm filter` (src/bin/coverm.rs:408-472): ReferenceSortedBamFilter (src/filter.rs:36-234) as a record sink ----

@@ -47,6 +47,7 @@ typedef struct cmbh_sample_info {
   uint32_t tid_begin, tid_end; /* contigs this rank owned for the sample */
   uint32_t decode_second_pass_blocks; /* blocks the first device inflate pass declined or timed out on */
   double gather_s;           /* summary exchange + table gather (wall clock) */
+  float decode_copy_enqueue_wall_ms, decode_host_wall_ms; /* host wall clocks inside cmb_submit_bgzf (diagnostics) */
 } cmbh_sample_info;
 
 typedef struct cmbh_result {
