@@ -279,6 +279,8 @@ def main():
     # (every rank decodes only its BGZF block range; one NCCL gather of the per-contig table inside the library).
     # --scaling weak: N different samples, one per GPU, no exchange at all (replicas).
     strong = world > 1 and args.scaling == "strong"
+    if strong:
+        threads = ncpu  # after the gather only rank 0 works on the host (estimator replay + printing): it gets every core
     file_rank = 0 if strong else rank
     bam = os.path.join(args.workdir, f"sample_c{args.config}_r{file_rank}_{args.contigs}_{args.reads}.bam")
     if not strong or rank == 0:

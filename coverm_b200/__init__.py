@@ -104,7 +104,7 @@ class Tuples(C.Structure):
                 ("iv_start", C.POINTER(C.c_int32)), ("iv_len", C.POINTER(C.c_int32))]
 
 
-HOST_SYMBOLS = ["cmbh_session_create", "cmbh_session_destroy", "cmbh_last_error", "cmbh_session_set_shard", "cmbh_session_set_group", "cmbh_session_ctx",
+HOST_SYMBOLS = ["cmbh_session_create", "cmbh_session_destroy", "cmbh_last_error", "cmbh_session_set_shard", "cmbh_session_set_group", "cmbh_session_set_group_output", "cmbh_session_ctx",
                 "cmbh_run", "cmbh_plan_params", "cmbh_free_result", "cmbh_main", "cmbh_extract_tuples", "cmbh_free_tuples"]
 
 
@@ -186,6 +186,7 @@ def load_library(path=None):
     lib.cmbh_run.argtypes = [C.c_void_p, C.c_int, C.POINTER(C.c_char_p), C.POINTER(MemInput), C.c_int,
                              C.POINTER(HostResult)]
     lib.cmb_last_bgzf_batch.argtypes = [C.c_void_p, C.POINTER(ReadBatch), C.POINTER(C.c_uint32), C.POINTER(C.c_uint32)]
+    lib.cmbh_session_set_group_output.argtypes = [C.c_void_p, C.c_int]
     lib.cmbh_session_set_group.argtypes = [C.c_void_p, C.c_int, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p]
     lib.cmb_comm_unique_id.argtypes = [C.c_void_p]
     lib.cmb_allgather_stats.argtypes = [C.c_void_p, C.POINTER(C.c_uint32), C.POINTER(C.c_uint64), C.c_void_p, C.c_void_p]
@@ -246,6 +247,9 @@ class Session:
 
     def set_shard(self, tid_begin, tid_end):
         self._lib.cmbh_session_set_shard(self._h, tid_begin, tid_end)
+
+    def set_group_output(self, every_rank_prints):
+        self._lib.cmbh_session_set_group_output(self._h, 1 if every_rank_prints else 0)
 
     def set_group(self, rank, n_ranks, nccl_id=None, allgather=None):
         """Make this session rank `rank` of `n_ranks` processing every sample together (contig sharding).  `nccl_id`: the 128

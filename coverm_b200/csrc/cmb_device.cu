@@ -935,7 +935,19 @@ void* cmb_stream(cmb_ctx* c) { return c ? (void*)c->stream : nullptr; }
     if (r_ != ncclSuccess) return fail(ctx, CMB_E_CUDA, "%s failed: %s (%s:%d)", #expr, ncclGetErrorString(r_), __FILE__, __LINE__); \
   } while (0)
 
+namespace {
+// NCCL writes its banner / debug lines to stdout by default; stdout carries the coverage table.
+void nccl_output_to_stderr() {
+  static const bool once = [] {
+    if (!getenv("NCCL_DEBUG_FILE")) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
+    return true;
+  }();
+  (void)once;
+}
+}  // namespace
+
 int cmb_comm_unique_id(uint8_t id[CMB_COMM_ID_BYTES]) {
+  nccl_output_to_stderr();
   static_assert(sizeof(ncclUniqueId) == CMB_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
   if (!id) return fail(nullptr, CMB_E_ARG, "cmb_comm_unique_id: null argument");
   ncclUniqueId u;
@@ -947,6 +959,7 @@ int cmb_comm_unique_id(uint8_t id[CMB_COMM_ID_BYTES]) {
 int cmb_comm_init(cmb_ctx* c, const uint8_t id[CMB_COMM_ID_BYTES], int rank, int n_ranks) {
   if (!c || !id || n_ranks < 1 || rank < 0 || rank >= n_ranks) return fail(c, CMB_E_ARG, "cmb_comm_init: bad arguments");
   if (c->comm) return fail(c, CMB_E_ARG, "cmb_comm_init: the context already has a communicator");
+  nccl_output_to_stderr();
   CU_TRY(c, cudaSetDevice(c->device));
   ncclUniqueId u;
   memcpy(&u, id, sizeof u);
@@ -964,6 +977,7 @@ int cmb_comm_init_local(cmb_ctx* const* ctxs, int n_ranks) {
     devs[r] = ctxs[r]->device;
   }
   std::vector<ncclComm_t> comms(n_ranks);
+  nccl_output_to_stderr();
   NCCL_TRY(ctxs[0], ncclCommInitAll(comms.data(), n_ranks, devs.data()));
   auto barrier = std::make_shared<LocalBarrier>();
   barrier->n = n_ranks;
@@ -1098,31 +1112,39 @@ constexpr uint64_t DEC_TAIL_BYTES = 4u << 20;  // ranged decode: inflated bytes 
 
 // Launch the inflate kernel over blocks [a.b0, a.b1).  CMB_INFLATE selects the first-pass kernel: t1 (default: one thread
 // per block + kd_crc32), g8 (four blocks per warp) or w1 (one block per warp, also the second pass over declined blocks).
-int inflate_kind() {  // CMB_INFLATE: t1 (default) | g8 | w1
-  static const int which = [] {
+// First-pass inflate kernel: 0 = kd_inflate_t1 (a thread per block), 1 = kd_inflate_g8 (four blocks per warp), 2 = kd_inflate (a
+// warp per block).  t1 has the higher THROUGHPUT (its ~75 000 streams in flight need that many blocks) but every block takes
+// ~50 ms however few there are; g8 finishes a block in ~20 ms.  So the choice follows the number of blocks: a whole 10 M-read
+// file (46 000 blocks) goes to t1, a rank's share of it on 4 or 8 GPUs to g8.  CMB_INFLATE=t1|g8|w1 overrides.
+constexpr uint32_t T1_MIN_BLOCKS = 28000;
+int inflate_kind(uint32_t n_blocks) {
+  static const int forced = [] {
     const char* e = getenv("CMB_INFLATE");
+    if (e && !strcmp(e, "t1")) return 0;
     if (e && !strcmp(e, "g8")) return 1;
     if (e && !strcmp(e, "w1")) return 2;
     if (getenv("CMB_INFLATE_G8") && getenv("CMB_INFLATE_G8")[0] == '0') return 2;
-    return 0;
+    return -1;
   }();
-  return which;
+  if (forced >= 0) return forced;
+  return n_blocks >= T1_MIN_BLOCKS ? 0 : 1;
 }
 // Default: ONE persistent launch whose threads poll the windows' arrival flags (bounded wait), so that every SM has work as soon
 // as the first window is in.  CMB_INFLATE_WINDOWS=1 (t1 only) launches per copied window instead, stream-ordered behind the
 // window's copy -- nothing on the device then waits for data, which tools that serialise streams (ncu, compute-sanitizer)
 // need; with the default 8 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS) those launches overlap poorly, hence not the default.
 bool inflate_per_window() {
-  static const bool v = inflate_kind() == 0 && getenv("CMB_INFLATE_WINDOWS") && getenv("CMB_INFLATE_WINDOWS")[0] == '1';
+  static const bool v = getenv("CMB_INFLATE_WINDOWS") && getenv("CMB_INFLATE_WINDOWS")[0] == '1';
   return v;
 }
 int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first_pass = true) {
-  const int which = inflate_kind();
+  const int which = inflate_kind(a.b1 - a.b0);
   const int k = (first_pass && !a.block_list) ? which : 2;
   const uint32_t nb = a.b1 - a.b0;
   if (k == 0) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
-    const uint32_t grid = std::min<uint32_t>((nb + T1_THREADS - 1) / T1_THREADS, (uint32_t)c->sm_count * 5);
+    uint32_t grid = std::min<uint32_t>((nb + T1_THREADS - 1) / T1_THREADS, (uint32_t)c->sm_count * 5);
+    if (const char* cap = getenv("CMB_T1_MAX_CTAS")) grid = std::max<uint32_t>(1, std::min<uint32_t>(grid, (uint32_t)atoi(cap)));  // experiment knob: fewer live streams
     kd_inflate_t1<<<grid, T1_THREADS, T1_SMEM_BYTES, st>>>(a);
     CU_TRY(c, cudaGetLastError());
     kd_crc32<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)c->sm_count * 8), 256, 0, st>>>(a);

@@ -377,10 +377,11 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
         if (m.path == path) in = m;
       inputs.push_back(in);
     }
+    const bool output_rank = !shared_session || shared_session->is_output_rank();  // multi-GPU: only rank 0 prints
     CoverageTaker taker = plan.taker == Plan::TakerKind::Streaming ? CoverageTaker::streaming(os)
                           : plan.taker == Plan::TakerKind::Pileup  ? CoverageTaker::pileup(os)
                                                                    : CoverageTaker::cached(plan.estimators.size());
-    if (!o.lib_streaming) {  // EstimatorsAndTaker::print_headers (coverm.rs:1506-1519)
+    if (!o.lib_streaming && output_rank) {  // EstimatorsAndTaker::print_headers (coverm.rs:1506-1519)
       std::vector<std::string> headers;
       for (auto& e : plan.estimators)
         for (auto& h : e.column_headers()) headers.push_back(h);
@@ -401,7 +402,7 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
     }
     plan.printer.pool = &session->pool();
     const double t_driver0 = now_s();
-    DriverIO io{session, plan.params, &res.timings, &res.record_counts, o.quiet ? nullptr : &err};
+    DriverIO io{session, plan.params, &res.timings, &res.record_counts, (o.quiet || !output_rank) ? nullptr : &err};
     if (o.sub == "contig") {
       if (gene_definitions) res.reads_mapped = gene_coverage(inputs, taker, plan.estimators, *gene_definitions, nullptr, !o.no_zeros, io);
       else res.reads_mapped = contig_coverage(inputs, taker, plan.estimators, !o.no_zeros, io);
@@ -443,7 +444,7 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
       }
     }
     const double t_print0 = now_s();
-    plan.printer.finalise_printing(taker, *os, res.reads_mapped, plan.columns_to_normalise, plan.rpkm_column, plan.tpm_column);
+    if (output_rank) plan.printer.finalise_printing(taker, *os, res.reads_mapped, plan.columns_to_normalise, plan.rpkm_column, plan.tpm_column);
     os->flush();
     if (o.timing) err << "#timing_run\tdrivers_s=" << (t_print0 - t_driver0) << "\tprint_s=" << (now_s() - t_print0) << '\n';
     if (o.print_reads_mapped)

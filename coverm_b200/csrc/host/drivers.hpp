@@ -142,6 +142,10 @@ inline std::vector<ReadsMapped> contig_coverage(const std::vector<InputSpec>& ba
   const bool csr = io.params.want & CMB_WANT_HIST_CSR;
   for (const InputSpec& in : bam_readers) {
     const SampleResult r = run_sample(io, in);
+    if (!io.session->is_output_rank()) {  // a non-printing rank of a multi-GPU group: its part ended with the gather
+      reads_mapped_vector.push_back({0, r.num_detected_primary_alignments});
+      continue;
+    }
     coverage_taker.start_stoit(r.stoit_name);
     uint64_t num_mapped_reads_total = 0;
     const uint32_t n = (uint32_t)r.header().names.size();
@@ -254,6 +258,10 @@ inline std::vector<ReadsMapped> gene_coverage(const std::vector<InputSpec>& bam_
   const std::vector<uint64_t> contig_mode_unobserved{0};  // calculate_coverage(&[0]), genes.rs:536-539
   for (const InputSpec& in : bam_readers) {
     const SampleResult r = run_sample(io, in);
+    if (!io.session->is_output_rank()) {  // a non-printing rank of a multi-GPU group: its part ended with the gather
+      reads_mapped_vector.push_back({0, r.num_detected_primary_alignments});
+      continue;
+    }
     coverage_taker.start_stoit(r.stoit_name);
     const ResolvedGenes& genes = *r.genes;
     const uint32_t n = (uint32_t)r.header().names.size();
@@ -311,6 +319,10 @@ inline std::vector<ReadsMapped> mosdepth_genome_coverage_with_contig_names(
   const size_t n_genomes = contigs_and_genomes.genomes.size();
   for (const InputSpec& in : bam_readers) {
     const SampleResult r = run_sample(io, in);
+    if (!io.session->is_output_rank()) {  // a non-printing rank of a multi-GPU group: its part ended with the gather
+      reads_mapped_vector.push_back({0, r.num_detected_primary_alignments});
+      continue;
+    }
     coverage_taker.start_stoit(r.stoit_name);
     const uint32_t n = (uint32_t)r.header().names.size();
     std::vector<int64_t> genome_of(n, -1);
@@ -460,6 +472,10 @@ inline std::vector<ReadsMapped> mosdepth_genome_coverage(const std::vector<Input
   const bool csr = io.params.want & CMB_WANT_HIST_CSR;
   for (const InputSpec& in : bam_readers) {
     const SampleResult r = run_sample(io, in);
+    if (!io.session->is_output_rank()) {  // a non-printing rank of a multi-GPU group: its part ended with the gather
+      reads_mapped_vector.push_back({0, r.num_detected_primary_alignments});
+      continue;
+    }
     coverage_taker.start_stoit(r.stoit_name);
     const Header& h = r.header();
     const Walk walk{h, split_char, single_genome};

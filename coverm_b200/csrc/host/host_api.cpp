@@ -107,6 +107,12 @@ int cmbh_session_set_group(cmbh_session* s, int rank, int n_ranks, const uint8_t
   }
 }
 
+int cmbh_session_set_group_output(cmbh_session* s, int every_rank_prints) {
+  if (!s) return -2;
+  s->dev->set_every_rank_prints(every_rank_prints != 0);
+  return 0;
+}
+
 void* cmbh_session_ctx(cmbh_session* s) { return s ? (void*)s->dev->ctx() : nullptr; }
 
 int cmbh_run(cmbh_session* s, int argc, const char* const* argv, const cmbh_mem_input* mem, int n_mem, cmbh_result* res) {

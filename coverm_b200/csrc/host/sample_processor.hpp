@@ -246,6 +246,11 @@ class DeviceSession {
   }
   int group_rank() const { return group_rank_; }
   int group_size() const { return group_n_; }
+  // After the gather every rank holds the complete table, but only one needs to turn it into text: rank 0 replays the
+  // estimators and prints, the others return an empty table -- unless every_rank_prints (tests: proves the gather is complete
+  // everywhere).
+  void set_every_rank_prints(bool v) { every_rank_prints_ = v; }
+  bool is_output_rank() const { return group_n_ <= 1 || group_rank_ == 0 || every_rank_prints_; }
 
   // One sample.  In a group every rank must call this for the same input (it is collective).
   SampleResult process(const InputSpec& in, const cmb_params& params) {
@@ -787,7 +792,7 @@ class DeviceSession {
   std::vector<std::string> gene_cache_names_;
   // group (multi-GPU contig sharding)
   int group_rank_ = 0, group_n_ = 1;
-  bool group_nccl_ = false;
+  bool group_nccl_ = false, every_rank_prints_ = false;
   AllGatherFn group_fn_ = nullptr;
   void* group_user_ = nullptr;
   std::vector<cmb_hist_pair> local_pairs_;

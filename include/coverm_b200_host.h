@@ -73,8 +73,8 @@ int cmbh_session_set_shard(cmbh_session* s, uint32_t tid_begin, uint32_t tid_end
  * make this session rank `rank` of `n_ranks`.  Every following cmbh_run is then COLLECTIVE -- each rank calls it with the
  * same argv -- and per sample each rank owns a contig range (balanced by length), uploads and inflates only the BGZF
  * blocks holding it, and one gather completes the per-contig table on every rank, after which the drivers and printers run
- * as on one GPU (global scalars in entry order, src/contig.rs:70-72, src/coverage_printer.rs:457-465): every rank
- * returns the same text; a caller normally keeps rank 0's.
+ * as on one GPU (global scalars in entry order, src/contig.rs:70-72, src/coverage_printer.rs:457-465) on rank 0, whose
+ * cmbh_run returns the text (see cmbh_session_set_group_output).
  *   nccl_id != NULL : the gather runs over NCCL inside the library (id from cmb_comm_unique_id on rank 0, shared by the
  *                     caller -- torch.distributed broadcast, MPI, a file);
  *   nccl_id == NULL : `allgather(user, send, bytes_per_rank, recv)` is the caller's own all-gather of host buffers
@@ -82,6 +82,10 @@ int cmbh_session_set_shard(cmbh_session* s, uint32_t tid_begin, uint32_t tid_end
  * n_ranks == 1 leaves the group. */
 typedef int (*cmbh_allgather_fn)(void* user, const void* send, size_t bytes_per_rank, void* recv);
 int cmbh_session_set_group(cmbh_session* s, int rank, int n_ranks, const uint8_t* nccl_id, cmbh_allgather_fn allgather, void* user);
+/* After the gather every rank holds the complete table; by default only rank 0 turns it into text (the other ranks' cmbh_run
+ * returns an empty table, status 0).  every_rank_prints != 0 makes all of them print -- the tests use it to show that the
+ * gathered table is complete on every rank. */
+int cmbh_session_set_group_output(cmbh_session* s, int every_rank_prints);
 
 /* The session's device context (a cmb_ctx* of coverm_b200.h), for callers that continue on the device ABI after a
  * cmbh_run -- e.g. re-running the kernels over the tuples the run left in HBM (cmb_last_bgzf_batch). */

@@ -103,6 +103,7 @@ def allgather(send):  # the caller-supplied host all-gather of cmbh_session_set_
 
 sess = coverm_b200.Session(device=0, threads=2, lib=lib)
 sess.set_group(rank, world, allgather=allgather)
+sess.set_group_output(every_rank_prints=(os.environ.get("RANK0_ONLY") != "1"))
 results = []
 for argv in runs:
     r = sess.run(argv + ["-t", "2", "--print-reads-mapped"])
@@ -196,3 +197,12 @@ def test_group_mode_errors_are_collective(tmp_path):
         rc, out, rm = _oracle(argv)
         for r in range(2):
             assert res[r][i]["status"] == rc and res[r][i]["out"] == out, (argv, r, res[r][i]["err"])
+
+
+def test_group_mode_only_rank0_prints_by_default(tmp_path, group_bams):
+    runs = GROUP_RUNS(group_bams)[:2]
+    res = _run_group(tmp_path, 2, runs, env={"CMB_EMU_BGZF": "1", "RANK0_ONLY": "1"})
+    for i, argv in enumerate(runs):
+        rc, out, rm = _oracle(argv)
+        assert res[0][i]["status"] == rc and res[0][i]["out"] == out and res[0][i]["rm"] == rm
+        assert res[1][i]["status"] == 0 and res[1][i]["out"] == ""
