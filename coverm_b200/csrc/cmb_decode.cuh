@@ -427,8 +427,11 @@ __global__ void __launch_bounds__(INF_WARPS * 32, 2) kd_inflate(const InflateArg
     if (a.ready) {
       const volatile uint32_t* flag = a.ready + a.block_window[b];
       uint32_t spins = 0;
-      while (*flag == 0 && spins < (1u << 24)) {  // bounded (~5 s): a copy that never lands must not hang the GPU
-        __nanosleep(256);
+      unsigned long long waited_ns = 0;
+      while (*flag == 0 && waited_ns < 4000000000ull) {  // bounded (4 s): a copy that never lands must not hang the GPU
+        const uint32_t ns = 256u << min(spins, 7u);      // back-off: see kd_inflate_t1
+        __nanosleep(ns);
+        waited_ns += ns;
         ++spins;
       }
       arrived = __all_sync(FULL, *flag != 0);

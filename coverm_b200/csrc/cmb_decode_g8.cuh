@@ -290,8 +290,11 @@ __global__ void __launch_bounds__(G8_WARPS * 32, 2) kd_inflate_g8(const InflateA
       const volatile uint32_t* flag = a.ready + (have ? a.block_window[b] : 0);
       uint32_t spins = 0;
       arrived = !have || *flag != 0;
-      while (!__all_sync(FULL, arrived) && spins < (1u << 22)) {
-        __nanosleep(256);
+      unsigned long long waited_ns = 0;
+      while (!__all_sync(FULL, arrived) && waited_ns < 2000000000ull) {  // back-off: polling must not crowd out the copy engine's writes
+        const uint32_t ns = 256u << min(spins, 7u);
+        __nanosleep(ns);
+        waited_ns += ns;
         ++spins;
         arrived = !have || *flag != 0;
       }

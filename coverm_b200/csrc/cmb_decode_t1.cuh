@@ -148,6 +148,7 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
   enum : uint32_t { IDLE, WAIT, HDR, SYM, FIN };
   uint32_t state = IDLE;
   uint32_t b = 0, n_out = 0, op = 0, bfinal = 0, spins = 0;
+  unsigned long long waited_ns = 0;
   const uint8_t* in_end = nullptr;
   uint8_t* out = nullptr;
 
@@ -158,6 +159,7 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
       if (tk >= a.b1 - a.b0) return;
       b = a.block_list ? a.block_list[tk] : a.b0 + tk;
       spins = 0;
+      waited_ns = 0;
       state = WAIT;
     }
     if (state == WAIT) {
@@ -177,12 +179,18 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
           br.init(in);
           state = HDR;
         }
-      } else if (++spins > (1u << 20)) {  // the window never came (copy failure, a profiler serialising the streams)
+      } else if (waited_ns > 2000000000ull) {  // 2 s: the window never came (copy failure, a profiler serialising the streams)
         a.status[b] = 31u;
         atomicAdd(a.fail_count, 1u);
         state = IDLE;
       } else {
-        __nanosleep(200);
+        // Exponential back-off, 0.25 us .. 32 us.  Tens of thousands of threads polling a handful of window flags every few
+        // hundred ns hammer one L2 slice so hard that the copy engine's own writes (the data AND the flags) queue behind the
+        // polls: on a 9 GB file that turned a 0.3 s decode into 2 s of time-outs.
+        const uint32_t ns = 256u << min(spins, 7u);
+        __nanosleep(ns);
+        waited_ns += ns;
+        ++spins;
       }
     }
     uint32_t st = 0;  // the check that declined the block, 0 = fine

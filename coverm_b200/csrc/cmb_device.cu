@@ -1526,6 +1526,13 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
   out->h2d_bytes = (byte_hi - byte_lo) + 24ull * nb + 8;
   if (first_err.load()) return fail(c, CMB_E_CUDA, "cmb_submit_bgzf: copy/inflate stage failed: %s", cudaGetErrorString((cudaError_t)first_err.load()));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(c->stream, d.done_events[t], 0));
+  if (getenv("CMB_PIPELINE_STATS")) {  // how long the window copies alone took (the done events carry no timing: time them on the host)
+    const auto h0 = std::chrono::steady_clock::now();
+    for (uint32_t t = 0; t < T; ++t) cudaEventSynchronize(d.done_events[t]);
+    const double wait_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - h0).count();
+    fprintf(stderr, "#decode_h2d\twindows=%zu\tbytes=%llu\tcopy_streams_done_after_ms=%.1f (host clock from the end of the enqueue; enqueue took %.1f ms)\n",
+            windows.size(), (unsigned long long)(byte_hi - byte_lo), wait_ms, copy_wall_ms);
+  }
   if (per_window) {
     for (size_t k = 0; k < std::min<size_t>(NCS, windows.size()); ++k) {
       CU_TRY(c, cudaEventRecord(d.cstream_done[k], d.cstreams[k]));
@@ -1562,7 +1569,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     CU_TRY(c, cudaMemcpy(status.data(), d.d_status, 4ull * nb, cudaMemcpyDeviceToHost));
     if (getenv("CMB_DECODE_RETRY_TEST"))  // testing aid: pretend every 7th block was declined by the first pass (code 29)
       for (uint32_t b = first_block; b < data_end; b += 7) status[b] = 29;
-    if (getenv("CMB_DECODE_VERIFY")) {
+    if (getenv("CMB_DECODE_VERIFY") || getenv("CMB_PIPELINE_STATS")) {
       uint32_t hist[32] = {0};
       for (uint32_t b = 0; b < nb; ++b) hist[std::min<uint32_t>(status[b], 31)]++;
       fprintf(stderr, "#decode_status");

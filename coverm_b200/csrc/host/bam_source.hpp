@@ -184,6 +184,8 @@ class InflateStream {
     return true;
   }
   void set_window(size_t window_bytes) { window_ = window_bytes; }
+  bool is_bgzf() const { return kind_ == BGZF; }
+  size_t compressed_consumed() const { return off_; }  // BGZF: file bytes behind everything fill() has returned so far
   uint64_t compressed_bytes() const { return n_; }
   // uncompressed / fully inflated inputs: the raw byte range (BlockIndex cuts it into slices)
   bool is_raw() const { return kind_ == RAW; }

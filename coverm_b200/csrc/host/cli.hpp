@@ -455,7 +455,8 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
       for (size_t i = 0; i < res.timings.size(); ++i) {
         const SampleTiming& t = res.timings[i];
         err << "#timing\tsample=" << i << "\trecords=" << res.record_counts[i] << "\ttotal_s=" << t.total_s << "\tdecode_s=" << t.decode_s
-            << "\tsubmit_wait_s=" << t.submit_wait_s << "\tend_sample_s=" << t.end_sample_s << "\tk0_ms=" << t.device.ms_zero
+            << "\tsubmit_wait_s=" << t.submit_wait_s << "\tend_sample_s=" << t.end_sample_s << "\theader_s=" << t.header_s << "\tindex_s=" << t.index_s
+            << "\tdevice_call_s=" << t.device_call_s << "\tgather_s=" << t.gather_s << "\tk0_ms=" << t.device.ms_zero
             << "\tk1_ms=" << t.device.ms_accumulate << "\tk2_ms=" << t.device.ms_scan << "\tk3_ms=" << t.device.ms_finalize << '\n';
       }
     res.status = 0;

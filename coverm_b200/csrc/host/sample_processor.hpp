@@ -26,6 +26,7 @@ inline std::string file_stem(const std::string& path) {  // Path::file_stem (bam
 
 struct SampleTiming {
   double total_s = 0, decode_s = 0, submit_wait_s = 0, end_sample_s = 0;
+  double header_s = 0, index_s = 0, device_call_s = 0;  // inside decode_s: header parse, BGZF block index (+ range probes), cmb_submit_bgzf
   cmb_sample_timing device{};
   uint64_t h2d_bytes = 0;
   bool device_decode = false;
@@ -440,6 +441,15 @@ class DeviceSession {
     //      the parsed copy of the previous sample is reused then (500 000 names are not rebuilt per sample).
     uint64_t records_at = 0;
     uint32_t n_ref = 0;
+    // Fastest case: the file starts with the very same COMPRESSED bytes as the previous sample's header did (the same file
+    // again, or samples written by one pipeline): nothing is inflated on the host at all.
+    bool hdr_fast = false;
+    if (hdr_cache_ && stream.is_bgzf() && !hdr_comp_.empty() && n >= hdr_comp_.size() && memcmp(p, hdr_comp_.data(), hdr_comp_.size()) == 0) {
+      hdr_fast = true;
+      res.hdr = hdr_cache_;
+      n_ref = (uint32_t)res.hdr->names.size();
+      records_at = hdr_records_at_;
+    } else {
     if (!need(12) || memcmp(buf.data() + begin, "BAM\1", 4) != 0) throw Panic("Error reading BAM header: not a BAM/SAM file: " + in.path);
     const uint32_t l_text = rd_u32(buf.data() + begin + 4);
     if (!need(12 + (size_t)l_text)) throw Panic("Error reading BAM header: truncated");
@@ -466,7 +476,10 @@ class DeviceSession {
       hdr_raw_.assign(buf.data() + begin + refs_at, buf.data() + begin + o);
       hdr_cache_ = res.hdr;
     }
+    hdr_comp_.clear();  // refreshed below, once the block index is known
     begin += records_at;
+    }
+    res.timing.header_s = now_s() - t0;
 
     // ---- device reference + params
     uint32_t sb = std::min<uint32_t>(shard_begin_, n_ref), se = std::min<uint32_t>(shard_end_, n_ref);
@@ -554,9 +567,24 @@ class DeviceSession {
     bool decoded_on_device = false;
     {
       // region-parallel pipeline (decode_runner.hpp): this thread only acquires / submits staging batches
+      const double t_index0 = now_s();
       BlockIndex bx;
       if (stream.is_raw()) bx.build(stream.raw_data(), stream.raw_size());
       else bx.build(p, n);
+      res.timing.index_s = now_s() - t_index0;
+      if (!hdr_fast && bx.bgzf && !stream.is_raw()) {
+        // htslib flushes the BGZF block after the header (bam_hdr_write), so the records usually start a block: then the
+        // compressed bytes in front of that block ARE the header, and the next sample that begins with the same bytes needs no
+        // header inflate at all.
+        const size_t b = (size_t)(std::lower_bound(bx.ustart.begin(), bx.ustart.end(), records_at) - bx.ustart.begin());
+        if (b > 0 && b < bx.blocks.size() && bx.ustart[b] == records_at && bx.blocks[b].cdata >= 18) {
+          const size_t start = bx.blocks[b].cdata - 18;
+          if (start <= (256u << 20) && p[start] == 0x1f && p[start + 1] == 0x8b) {
+            hdr_comp_.assign(p, p + start);
+            hdr_records_at_ = records_at;
+          }
+        }
+      }
       // Device-side decode first (compressed blocks cross PCIe, the GPU inflates and parses them); the host pipeline
       // below runs when the input is not BGZF, when CMB_HOST_DECODE is set, or when the device declines the stream.  Pair
       // filtering included: the device matches mates itself (cmb_pairs.cuh); the host's BTreeMap-style matching further
@@ -603,7 +631,9 @@ class DeviceSession {
         }
         cmb_bgzf_result br{};
         const double a = now_s();
+        res.timing.index_s = now_s() - t_index0;  // incl. the block table and, in a group, the range probes
         const int r2 = range_ok ? cmb_submit_bgzf(ctx_, &bi, &br) : CMB_E_DECLINED;
+        res.timing.device_call_s = now_s() - a;
         if (r2 == CMB_OK) {
           decoded_on_device = true;
           res.timing.device_decode = true;
@@ -643,6 +673,10 @@ class DeviceSession {
         fprintf(stderr, "#pipeline\titems=%u\tworkers=%u\tinflate_s=%.3f\tchain_s=%.3f\textract_s=%.3f\tidle_s=%.3f (summed over workers)\n",
                 pc.n_items, pc.n_workers, pc.inflate_s, pc.scan_s, pc.extract_s, pc.idle_s);
       }
+    }
+    if (pair_mode && !decoded_on_device && hdr_fast) {  // the header was recognised without inflating it: skip over it now
+      if (!need((size_t)records_at)) throw Panic("Error reading BAM header: truncated");
+      begin = (size_t)records_at;
     }
     if (pair_mode && !decoded_on_device) stream.set_window(48u << 20);  // mate matching is sequential: decode window by window
     if (pair_mode && !decoded_on_device) for (;;) {
@@ -777,6 +811,8 @@ class DeviceSession {
 
   std::shared_ptr<Header> hdr_cache_;  // parsed reference list of the previous sample and its raw bytes (n_ref .. first record)
   std::vector<uint8_t> hdr_raw_;
+  std::vector<uint8_t> hdr_comp_;  // the compressed file prefix the last full header parse consumed, and where its records start
+  uint64_t hdr_records_at_ = 0;
   cmb_contig_stats* rows_buf_ = nullptr;
   size_t rows_cap_ = 0;
   ThreadPool pool_;

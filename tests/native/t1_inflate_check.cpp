@@ -10,6 +10,7 @@
 #include <random>
 #include <string>
 #include <vector>
+#include <algorithm>
 
 #define __device__
 #define __global__
@@ -31,6 +32,7 @@ template <class T> static inline T __ldcg(const T* p) { return *p; }
 static inline uint32_t atomicAdd(uint32_t* p, uint32_t v) { uint32_t o = *p; *p += v; return o; }
 static inline void __threadfence_system() {}
 static inline void __nanosleep(unsigned) {}
+using std::min;
 static const uint8_t c_clen_order[19] = {16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15};
 struct InflateArgs {
   const uint8_t* comp; const uint64_t* coff; const uint32_t* clen; const uint32_t* isize; const uint64_t* uoff;
