@@ -119,6 +119,19 @@ __device__ __forceinline__ bool t1_build(LenOf len_of, uint32_t n, Put put, int1
   return ok;
 }
 
+constexpr unsigned long long T1_WAIT_NS = 2000000000ull;  // bounded wait for a window, wall clock
+#ifndef T1_HOST_TEST
+__device__ __forceinline__ unsigned long long t1_now_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void t1_lane_busy(volatile uint32_t* w, int d) { atomicAdd(const_cast<uint32_t*>(w), (uint32_t)d); }
+#else
+static inline unsigned long long t1_now_ns() { return 0; }
+static inline void t1_lane_busy(volatile uint32_t* w, int d) { *w += (uint32_t)d; }
+static inline void __syncwarp() {}
+#endif
 __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs a) {
   extern __shared__ __align__(16) uint8_t t1_smem[];
   T1Stream& S = reinterpret_cast<T1Stream*>(t1_smem)[threadIdx.x];
@@ -147,8 +160,16 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
   };
   enum : uint32_t { IDLE, WAIT, HDR, SYM, FIN };
   uint32_t state = IDLE;
-  uint32_t b = 0, n_out = 0, op = 0, bfinal = 0, spins = 0;
-  unsigned long long waited_ns = 0;
+  uint32_t b = 0, n_out = 0, op = 0, bfinal = 0, spins = 0, skip = 0;
+  unsigned long long wait_t0 = 0;
+  // Lanes of one warp are in different states.  A lane whose window has not arrived must not hold up the lanes that are
+  // decoding (every trip round this loop is one symbol for them), so it sleeps only while NO lane of its warp decodes
+  // (t1_busy counts those) and otherwise just looks at the flag again some iterations later.
+  __shared__ uint32_t t1_busy[T1_THREADS / 32];
+  volatile uint32_t* const my_busy = t1_busy + (threadIdx.x >> 5);
+  if ((threadIdx.x & 31) == 0) *my_busy = 0;
+  __syncwarp();
+  bool counted = false;
   const uint8_t* in_end = nullptr;
   uint8_t* out = nullptr;
 
@@ -159,10 +180,13 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
       if (tk >= a.b1 - a.b0) return;
       b = a.block_list ? a.block_list[tk] : a.b0 + tk;
       spins = 0;
-      waited_ns = 0;
+      skip = 0;
+      wait_t0 = 0;
       state = WAIT;
     }
-    if (state == WAIT) {
+    if (state == WAIT && skip) {
+      --skip;
+    } else if (state == WAIT) {
       bool arrived = true;
       if (a.ready) arrived = *(const volatile uint32_t*)(a.ready + a.block_window[b]) != 0;
       if (arrived) {
@@ -178,19 +202,22 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
         } else {
           br.init(in);
           state = HDR;
+          t1_lane_busy(my_busy, 1);
+          counted = true;
         }
-      } else if (waited_ns > 2000000000ull) {  // 2 s: the window never came (copy failure, a profiler serialising the streams)
-        a.status[b] = 31u;
-        atomicAdd(a.fail_count, 1u);
-        state = IDLE;
       } else {
-        // Exponential back-off, 0.25 us .. 32 us.  Tens of thousands of threads polling a handful of window flags every few
-        // hundred ns hammer one L2 slice so hard that the copy engine's own writes (the data AND the flags) queue behind the
-        // polls: on a 9 GB file that turned a 0.3 s decode into 2 s of time-outs.
-        const uint32_t ns = 256u << min(spins, 7u);
-        __nanosleep(ns);
-        waited_ns += ns;
-        ++spins;
+        const unsigned long long now = t1_now_ns();
+        if (wait_t0 == 0) wait_t0 = now;
+        if (now - wait_t0 > T1_WAIT_NS) {  // the window never came (copy failure, a tool serialising the streams)
+          a.status[b] = 31u;
+          atomicAdd(a.fail_count, 1u);
+          state = IDLE;
+        } else if (*my_busy == 0) {  // the whole warp waits: back off, 0.25 .. 4 us, to keep the polls off the L2
+          __nanosleep(256u << (spins < 4u ? spins : 4u));
+          ++spins;
+        } else {
+          skip = 64;  // other lanes are decoding: no sleeping, look again 64 symbols later
+        }
       }
     }
     uint32_t st = 0;  // the check that declined the block, 0 = fine
@@ -424,6 +451,10 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
       a.status[b] = st;
       atomicAdd(a.fail_count, 1u);
       state = IDLE;
+    }
+    if (state == IDLE && counted) {
+      t1_lane_busy(my_busy, -1);
+      counted = false;
     }
   }
 }

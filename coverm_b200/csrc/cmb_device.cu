@@ -1137,7 +1137,16 @@ bool inflate_per_window() {
   static const bool v = getenv("CMB_INFLATE_WINDOWS") && getenv("CMB_INFLATE_WINDOWS")[0] == '1';
   return v;
 }
-int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first_pass = true) {
+// kd_crc32 over the blocks of `a` (the t1 path: its inflate kernel leaves the CRC to a second kernel)
+int launch_crc32(cmb_ctx* c, const InflateArgs& a, cudaStream_t st) {
+  const uint32_t nb = a.b1 - a.b0;
+  kd_crc32<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)c->sm_count * 8), 256, 0, st>>>(a);
+  CU_TRY(c, cudaGetLastError());
+  return CMB_OK;
+}
+// *crc_pending (when given) is set instead of launching kd_crc32: the caller launches it once nothing else has to get past it
+// in the hardware queue (a kernel waiting for its predecessor blocks the queue for every stream that shares it).
+int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first_pass = true, bool* crc_pending = nullptr) {
   const int which = inflate_kind(a.b1 - a.b0);
   const int k = (first_pass && !a.block_list) ? which : 2;
   const uint32_t nb = a.b1 - a.b0;
@@ -1147,7 +1156,8 @@ int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first
     if (const char* cap = getenv("CMB_T1_MAX_CTAS")) grid = std::max<uint32_t>(1, std::min<uint32_t>(grid, (uint32_t)atoi(cap)));  // experiment knob: fewer live streams
     kd_inflate_t1<<<grid, T1_THREADS, T1_SMEM_BYTES, st>>>(a);
     CU_TRY(c, cudaGetLastError());
-    kd_crc32<<<std::min<uint32_t>((nb + 7) / 8, (uint32_t)c->sm_count * 8), 256, 0, st>>>(a);
+    if (crc_pending) *crc_pending = true;
+    else if (int rc = launch_crc32(c, a, st)) return rc;
   } else if (k == 1) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_g8, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G8_SMEM_BYTES));
     const uint32_t per_cta = G8_WARPS * G8_STREAMS;
@@ -1433,6 +1443,8 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(d.streams[t], d.ev[1], 0));
   const bool per_window = inflate_per_window();
   const uint32_t NCS = 64;  // compute streams for the per-window launches
+  bool crc_pending = false;
+  InflateArgs persistent_args{};
   if (per_window) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
     while (d.cstreams.size() < std::min<size_t>(NCS, windows.size())) {
@@ -1455,7 +1467,14 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     // blocks before the one holding the first record are header text the host has already read: not inflated here
     a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
     a.block_window = d.d_block_window; a.ready = d.d_tickets + 1;
-    if ((rc = launch_inflate(c, a, c->stream))) return rc;
+    if (getenv("CMB_PREWARM")) {  // experiment: every copy stream has executed something before the persistent kernel starts
+      for (uint32_t t = 0; t < T; ++t) {
+        CU_TRY(c, cudaMemcpyAsync(d.d_cnt + 12, d.h_ones, 4, cudaMemcpyHostToDevice, d.streams[t]));
+        CU_TRY(c, cudaStreamSynchronize(d.streams[t]));
+      }
+    }
+    persistent_args = a;
+    if ((rc = launch_inflate(c, a, c->stream, true, &crc_pending))) return rc;
   }
   std::atomic<size_t> next_window{0};
   std::atomic<int> first_err{0};
@@ -1517,6 +1536,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
   }
   const double copy_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - copy_t0).count();
   out->ms_copy_enqueue_wall = (float)copy_wall_ms;
+  if (crc_pending && (rc = launch_crc32(c, persistent_args, c->stream))) return rc;  // every copy is enqueued: nothing left to hold up
   if (first_err.load()) {  // release the warps still waiting for windows that will never arrive
     cudaMemsetAsync(d.d_tickets + 1, 1, 4 * windows.size(), d.streams[0]);
     cudaStreamSynchronize(d.streams[0]);

@@ -72,7 +72,13 @@ __device__ __forceinline__ bool read_pair_passes(const RecView& a, const RecView
          __fsub_rn(1.0f, __fdiv_rn(edit_f, aligned_f)) >= p.min_percent_identity_pair;
 }
 
-__global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args a) {
+#ifndef CMB_K1_MINBLOCKS
+#define CMB_K1_MINBLOCKS 6
+#endif
+#ifndef CMB_K1_PREFETCH
+#define CMB_K1_PREFETCH 1  // issue the segment and first-interval loads right behind the column loads (one DRAM round trip less)
+#endif
+__global__ void __launch_bounds__(K1_THREADS, CMB_K1_MINBLOCKS) k1_filter_accumulate(const K1Args a) {
   const uint32_t i = blockIdx.x * K1_THREADS + threadIdx.x;
   const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const bool valid = i < a.n;
@@ -95,6 +101,25 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
     ivb = a.iv_begin[i];
     ive = a.iv_begin[i + 1];
   }
+#if CMB_K1_PREFETCH
+  // K1 is latency-bound (a thread's loads form the chain columns -> intervals -> segment table -> REDs).  The segment of a
+  // record depends on its tid only and its first aligned block on iv_begin only, so both are requested here, before the
+  // filter arithmetic and the block-wide sortedness scan, and are in registers by the time the events are added.
+  uint32_t pre_L = 0, pre_off0 = 0, pre_off1 = 0;
+  int32_t pre_s = INT_MIN, pre_n = 0;
+  const bool pre_seg = valid && !a.gene_first && tid >= 0 && (uint32_t)tid >= a.tid_begin && (uint32_t)tid < a.tid_end &&
+                       (uint32_t)tid < a.n_contigs;
+  if (pre_seg) {
+    const uint32_t lc = (uint32_t)tid - a.tid_begin;
+    pre_L = __ldg(a.len + lc);
+    pre_off0 = __ldg(a.off_span + lc);
+    pre_off1 = __ldg(a.off_span + lc + 1);
+  }
+  if (valid && ivb < ive) {
+    pre_s = __ldg(a.iv_start + ivb);
+    pre_n = __ldg(a.iv_len + ivb);
+  }
+#endif
   const bool unmapped = r.flag & 0x4, secondary = r.flag & 0x100, supplementary = r.flag & 0x800, proper = r.flag & 0x2;
   // FlagFilter::passes, lib.rs:67-78
   const bool flag_pass = !(secondary && !p.include_secondary) && !(supplementary && !p.include_supplementary) &&
@@ -190,10 +215,9 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
   }
 
   // +1 at `s` and -1 at `e` (when e lies inside the segment) of segment `lc`, plus the chunk tail sums K1b scans
-  auto add_events = [&](uint32_t lc, uint32_t s, uint64_t e) {
-    const uint32_t L = a.len[lc];
-    const uint64_t base = (uint64_t)a.off_span[lc] * SPAN;
-    const uint64_t end_padded = (uint64_t)a.off_span[lc + 1] * SPAN;  // first element of the next segment
+  auto add_events_in = [&](uint32_t L, uint32_t off0, uint32_t off1, uint32_t s, uint64_t e) {
+    const uint64_t base = (uint64_t)off0 * SPAN;
+    const uint64_t end_padded = (uint64_t)off1 * SPAN;  // first element of the next segment
     const uint64_t gs = base + s;
     const bool has_end = e < L;  // "True unless the read hits the contig end"
     atomicAdd(a.arena + gs, 1);
@@ -211,6 +235,7 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
       atomicAdd(a.tail_sum + ks, 1);
     }
   };
+  auto add_events = [&](uint32_t lc, uint32_t s, uint64_t e) { add_events_in(a.len[lc], a.off_span[lc], a.off_span[lc + 1], s, e); };
 
   if (a.gene_first) {
     // ---- per-gene coverage (genes.rs:182-344, 467-552).  A gene's delta array is the contig's, cut to [start, end) with the
@@ -318,16 +343,26 @@ __global__ void __launch_bounds__(K1_THREADS) k1_filter_accumulate(const K1Args 
   // ---- delta events (contig.rs:171-186)
   if (mine) {
     const uint32_t lc = (uint32_t)tid - a.tid_begin;
-    const uint32_t L = a.len[lc];
+    (void)lc;
+#if CMB_K1_PREFETCH
+    const uint32_t L = pre_L, off0 = pre_off0, off1 = pre_off1;
+#else
+    const uint32_t L = a.len[lc], off0 = a.off_span[lc], off1 = a.off_span[lc + 1];
+#endif
     for (uint32_t k = ivb; k < ive; ++k) {
+#if CMB_K1_PREFETCH
+      const int32_t s = k == ivb ? pre_s : a.iv_start[k];
+      const uint32_t n = (uint32_t)(k == ivb ? pre_n : a.iv_len[k]);
+#else
       const int32_t s = a.iv_start[k];
       const uint32_t n = (uint32_t)a.iv_len[k];
+#endif
       if (s == INT_MIN) continue;  // CMB_IV_PAD: unused slot of the interval pool
       if (s < 0 || (uint32_t)s >= L) {  // `ups_and_downs[cursor] += 1` would panic
         err |= ERR_BOUNDS;
         continue;
       }
-      add_events(lc, (uint32_t)s, (uint64_t)(uint32_t)s + n);
+      add_events_in(L, off0, off1, (uint32_t)s, (uint64_t)(uint32_t)s + n);
     }
   }
   err = __reduce_or_sync(FULL, err);

@@ -33,6 +33,14 @@ struct K2Args {
 };
 
 constexpr uint32_t K2_SMEM_STAGE_BYTES = K2_STAGES * CHUNK_BYTES;
+#if CMB_SPAN > 32
+typedef unsigned long long evmask_t;  // one bit per element of a span
+__device__ __forceinline__ uint32_t ev_first(evmask_t m) { return (uint32_t)__ffsll((long long)m) - 1; }
+#else
+typedef uint32_t evmask_t;
+__device__ __forceinline__ uint32_t ev_first(evmask_t m) { return (uint32_t)__ffs((int)m) - 1; }
+#endif
+static_assert(SPAN == 16 || SPAN == 32 || SPAN == 64, "a span is 16, 32 or 64 elements");
 constexpr uint32_t K2_SMEM_MISC = 64 /*barriers + tickets*/ + 2 * K2_WARPS * 8 /*warp aggregates, double-buffered*/;
 constexpr uint32_t K2_SMEM_BYTES_HIST = K2_SMEM_STAGE_BYTES + K2_SMEM_MISC + 2 * HIST_TOTAL * 4;
 constexpr uint32_t K2_SMEM_BYTES_NOHIST = K2_SMEM_STAGE_BYTES + K2_SMEM_MISC;
@@ -105,8 +113,18 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
   __syncthreads();
 
   constexpr uint32_t UNITS = SPAN / 4;                 // 16-byte units per span
-  const uint32_t row = (t * SPAN) / ROW_ELEMS;          // 128-byte tile row holding this thread's span
-  const uint32_t u0 = (t * UNITS) % (ROW_ELEMS / 4);    // its first unit within the row
+  const uint32_t row = (t * SPAN) / ROW_ELEMS;          // first 128-byte tile row of this thread's span
+  const uint32_t u0 = (t * UNITS) % (ROW_ELEMS / 4);    // its first unit within the row (0 unless SPAN < 32)
+  // A span of 64 is two tile rows, so the eight lanes of an LDS.128 phase sit on rows 0,2,..,14 and the 128B swizzle alone
+  // leaves lanes l and l+4 on the same banks.  Lanes 4..7 of every eight therefore visit their units in pairs swapped
+  // (unit j^1 when the others read unit j); the event mask is put back in position order after the loop.
+  const uint32_t swp = SPAN > 32 ? ((t >> 2) & 1u) : 0u;
+  // byte offset inside a stage tile of element e of this thread's span
+  auto elem_off = [&](uint32_t e) -> uint32_t {
+    const uint32_t idx = u0 + (e >> 2);
+    const uint32_t r = row + (idx >> 3);
+    return r * 128 + (((idx & 7) ^ (r & 7)) << 4) + ((e & 3) << 2);
+  };
   const uint32_t E = a.excl;
   uint32_t prev_chunk = 0, prev_slots = 0;
   uint32_t it = 0;
@@ -121,10 +139,13 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
 
     // ---- SPAN consecutive deltas per thread: LDS.128s through the 128B swizzle (conflict-free).
     //      Only their sum and the mask of non-zero positions stay in registers.
-    const uint8_t* rowp = smem + s * CHUNK_BYTES + row * 128;
+    const uint8_t* tilep = smem + s * CHUNK_BYTES;
+#if CMB_K2_COOP && CMB_SPAN == 32
+    const uint8_t* rowp = tilep + row * 128;
+#endif
     const uint32_t span = chunk * CHUNK_SPANS + t;
     int total = 0;
-    uint32_t ev = 0;
+    evmask_t ev = 0;
 #if CMB_K2_COOP && CMB_SPAN == 32
     {
       // Deltas are sparse (under 1 % of the positions; about three spans in four hold none), but a branch per thread saves
@@ -158,14 +179,21 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
 #else
     {
       int4* g = reinterpret_cast<int4*>(a.arena + (uint64_t)span * SPAN);
+      int4* g_even = g + swp;  // unit j^swp == j + swp for even j, j - swp for odd j
+      int4* g_odd = g - swp;
 #pragma unroll
       for (uint32_t j = 0; j < UNITS; ++j) {
-        const uint32_t unit = (u0 + j) ^ (row & 7);
-        const int4 q = *reinterpret_cast<const int4*>(rowp + unit * 16);
+        const uint32_t r = row + ((u0 + j) >> 3);
+        const uint32_t unit = (((u0 + j) & 7) ^ swp) ^ (r & 7);  // unit j^swp of the span, through the swizzle of its row
+        const int4 q = *reinterpret_cast<const int4*>(tilep + r * 128 + unit * 16);
         const uint32_t e4 = (q.x != 0 ? 1u : 0u) | (q.y != 0 ? 2u : 0u) | (q.z != 0 ? 4u : 0u) | (q.w != 0 ? 8u : 0u);
         total += (q.x + q.y) + (q.z + q.w);
-        ev |= e4 << (4 * j);
-        if (CLEAN && e4) g[j] = make_int4(0, 0, 0, 0);  // re-zero only the 16 B units that hold an event
+        ev |= (evmask_t)e4 << (4 * j);
+        if (CLEAN && e4) ((j & 1) ? g_odd : g_even)[j] = make_int4(0, 0, 0, 0);  // re-zero only the 16 B units that hold an event
+      }
+      if (SPAN > 32 && swp) {  // back to position order: swap neighbouring nibbles
+        constexpr evmask_t LO = (evmask_t)0x0f0f0f0f0f0f0f0full;
+        ev = ((ev & LO) << 4) | ((ev >> 4) & LO);
       }
     }
 #endif
@@ -295,13 +323,12 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
     if (ev) {
       int depth = carry;
       uint32_t from = 0;
-      uint32_t m = ev;
+      evmask_t m = ev;
       while (m) {
-        const uint32_t j = (uint32_t)__ffs(m) - 1;
+        const uint32_t j = ev_first(m);
         m &= m - 1;
         close_run(depth, from, j);
-        const uint32_t unit = (u0 + (j >> 2)) ^ (row & 7);
-        depth += *reinterpret_cast<const int*>(rowp + unit * 16 + (j & 3) * 4);  // the delta at position j
+        depth += *reinterpret_cast<const int*>(tilep + elem_off(j));  // the delta at position j
         from = j;
       }
       close_run(depth, from, SPAN);
