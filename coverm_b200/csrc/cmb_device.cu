@@ -1106,6 +1106,14 @@ void cmb_host_free(void* p) {
 namespace {
 constexpr size_t DEC_COPY_CHUNK = 8u << 20;    // pinned staging slot
 constexpr size_t DEC_WINDOW_BYTES = 32u << 20; // compressed bytes per copy+inflate window
+size_t dec_window_bytes() {  // CMB_DECODE_WINDOW_KB: testing aid, lets a small file span many windows
+  static const size_t v = [] {
+    const char* e = getenv("CMB_DECODE_WINDOW_KB");
+    const long kb = e ? atol(e) : 0;
+    return kb > 0 ? (size_t)kb << 10 : DEC_WINDOW_BYTES;
+  }();
+  return v;
+}
 constexpr size_t DEC_SLACK = 1024;
 constexpr size_t DEC_FRONT = 256;              // readable bytes in front of the first uploaded block (the bit readers align down)
 constexpr uint64_t DEC_TAIL_BYTES = 4u << 20;  // ranged decode: inflated bytes kept beyond the range for its last straddling record
@@ -1127,7 +1135,11 @@ int inflate_kind(uint32_t n_blocks) {
     return -1;
   }();
   if (forced >= 0) return forced;
-  return n_blocks >= T1_MIN_BLOCKS ? 0 : 1;
+  static const uint32_t min_blocks = [] {
+    const char* e = getenv("CMB_T1_MIN_BLOCKS");  // experiment knob
+    return e ? (uint32_t)atol(e) : T1_MIN_BLOCKS;
+  }();
+  return n_blocks >= min_blocks ? 0 : 1;
 }
 // Default: ONE persistent launch whose threads poll the windows' arrival flags (bounded wait), so that every SM has work as soon
 // as the first window is in.  CMB_INFLATE_WINDOWS=1 (t1 only) launches per copied window instead, stream-ordered behind the
@@ -1135,6 +1147,20 @@ int inflate_kind(uint32_t n_blocks) {
 // need; with the default 8 hardware queues (CUDA_DEVICE_MAX_CONNECTIONS) those launches overlap poorly, hence not the default.
 bool inflate_per_window() {
   static const bool v = getenv("CMB_INFLATE_WINDOWS") && getenv("CMB_INFLATE_WINDOWS")[0] == '1';
+  return v;
+}
+// Serial mode: copy everything, then ONE inflate launch ordered behind the copies on the context stream -- no flags, nothing on
+// the device waits for anything.  Used for files of a single window (nothing to overlap), on request (CMB_INFLATE_SERIAL=1),
+// and when a CUDA tool is injected into the process (ncu, compute-sanitizer: they serialise kernels against the other streams,
+// so a kernel that polls for copies would only ever see its bounded wait expire).
+bool inflate_serial_requested() {
+  static const bool v = [] {
+    if (const char* e = getenv("CMB_INFLATE_SERIAL")) return e[0] == '1';
+    for (const char* name : {"CUDA_INJECTION64_PATH", "NV_NSIGHT_INJECTION_PORT_BASE", "NV_COMPUTE_PROFILER_PERFWORKS_DIR", "NV_SANITIZER_INJECTION_PORT_BASE"})
+      if (const char* e = getenv(name))
+        if (e[0]) return true;
+    return false;
+  }();
   return v;
 }
 // kd_crc32 over the blocks of `a` (the t1 path: its inflate kernel leaves the CRC to a second kernel)
@@ -1379,7 +1405,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     while (b < data_end) {
       uint32_t e = b;
       uint64_t byte1 = byte0;
-      while (e < data_end && (e == b || in->block_coffset[e] + in->block_clen[e] + 8 - byte0 <= DEC_WINDOW_BYTES)) {
+      while (e < data_end && (e == b || in->block_coffset[e] + in->block_clen[e] + 8 - byte0 <= dec_window_bytes())) {
         byte1 = in->block_coffset[e] + in->block_clen[e] + 8;
         ++e;
       }
@@ -1389,11 +1415,12 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
       byte0 = byte1;
     }
   }
-  if (d.tickets_cap < windows.size() + 1 || !d.d_tickets) {
+  // [0] block ticket, [1, 1 + W) arrival flags, [1 + W] watermark, [2 + W, 3 + 2W] first block of each window
+  if (d.tickets_cap < 2 * windows.size() + 8 || !d.d_tickets) {
     cudaFree(d.d_tickets);
     d.d_tickets = nullptr;
     d.tickets_cap = 0;
-    const size_t want = windows.size() * 2 + 64;
+    const size_t want = windows.size() * 3 + 64;
     CU_TRY(c, cudaMalloc(&d.d_tickets, 4 * want));
     d.tickets_cap = want;
   }
@@ -1435,16 +1462,18 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
   CU_TRY(c, cudaMemsetAsync(d.d_cnt, 0, 64, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_status, 0, 4ull * nb, c->stream));
   CU_TRY(c, cudaMemcpyAsync(d.d_block_window, block_window.data(), 4ull * nb, cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * (windows.size() + 1), c->stream));
+  CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * (windows.size() + 2), c->stream));  // ticket, arrival flags, watermark
   CU_TRY(c, cudaMemsetAsync(infl_base + total, 0, DEC_SLACK, c->stream));
   CU_TRY(c, cudaMemsetAsync(comp_base + byte_hi, 0, DEC_SLACK, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_comp, 0, DEC_FRONT, c->stream));
   CU_TRY(c, cudaEventRecord(d.ev[1], c->stream));
   for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(d.streams[t], d.ev[1], 0));
-  const bool per_window = inflate_per_window();
+  const bool serial = !inflate_per_window() && (windows.size() <= 1 || inflate_serial_requested());
+  const bool per_window = !serial && inflate_per_window();
   const uint32_t NCS = 64;  // compute streams for the per-window launches
   bool crc_pending = false;
   InflateArgs persistent_args{};
+  std::vector<uint32_t> win_b0;  // outlives the asynchronous upload (pageable source: staged at the call)
   if (per_window) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
     while (d.cstreams.size() < std::min<size_t>(NCS, windows.size())) {
@@ -1461,12 +1490,19 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
       d.window_events.push_back(e);
     }
     for (size_t k = 0; k < std::min<size_t>(NCS, windows.size()); ++k) CU_TRY(c, cudaStreamWaitEvent(d.cstreams[k], d.ev[1], 0));
-  } else {  // one persistent launch over every block; its warps wait for their block's window to arrive
+  } else if (!serial) {  // one persistent launch over every block; its warps wait for their block's window to arrive
     InflateArgs a{};
     a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart; a.scratch = d.d_t1_scratch;
     // blocks before the one holding the first record are header text the host has already read: not inflated here
     a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
     a.block_window = d.d_block_window; a.ready = d.d_tickets + 1;
+    a.wm = d.d_tickets + 1 + windows.size(); a.win_b0 = d.d_tickets + 2 + windows.size(); a.n_windows = (uint32_t)windows.size();
+    {
+      win_b0.resize(windows.size() + 1);
+      for (size_t w = 0; w < windows.size(); ++w) win_b0[w] = windows[w].b0;
+      win_b0[windows.size()] = data_end;
+      CU_TRY(c, cudaMemcpyAsync(d.d_tickets + 2 + windows.size(), win_b0.data(), 4 * win_b0.size(), cudaMemcpyHostToDevice, c->stream));
+    }
     if (getenv("CMB_PREWARM")) {  // experiment: every copy stream has executed something before the persistent kernel starts
       for (uint32_t t = 0; t < T; ++t) {
         CU_TRY(c, cudaMemcpyAsync(d.d_cnt + 12, d.h_ones, 4, cudaMemcpyHostToDevice, d.streams[t]));
@@ -1537,6 +1573,13 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
   const double copy_wall_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - copy_t0).count();
   out->ms_copy_enqueue_wall = (float)copy_wall_ms;
   if (crc_pending && (rc = launch_crc32(c, persistent_args, c->stream))) return rc;  // every copy is enqueued: nothing left to hold up
+  if (serial && !first_err.load()) {
+    for (uint32_t t = 0; t < T; ++t) CU_TRY(c, cudaStreamWaitEvent(c->stream, d.done_events[t], 0));
+    InflateArgs a{};
+    a.comp = comp_base; a.coff = d.d_coff; a.clen = d.d_clen; a.isize = d.d_isize; a.uoff = d.d_ustart; a.scratch = d.d_t1_scratch;
+    a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
+    if ((rc = launch_inflate(c, a, c->stream))) return rc;
+  }
   if (first_err.load()) {  // release the warps still waiting for windows that will never arrive
     cudaMemsetAsync(d.d_tickets + 1, 1, 4 * windows.size(), d.streams[0]);
     cudaStreamSynchronize(d.streams[0]);

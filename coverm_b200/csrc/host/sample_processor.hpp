@@ -764,7 +764,7 @@ class DeviceSession {
     // device memory the buffers are enlarged and the kernels run again; otherwise the error stands.
     auto end_sample = [&](cmb_contig_stats* rows_out) {
       int r2 = cmb_end_sample(ctx_, rows_out, nullptr, 0, &n_pairs);
-      for (int attempt = 0; r2 == CMB_E_CAPACITY && decoded_on_device && attempt < 4; ++attempt) {
+      for (int attempt = 0; r2 == CMB_E_CAPACITY && decoded_on_device && attempt < 8; ++attempt) {
         cmb_read_batch again{};
         uint32_t nr = 0, ni = 0;
         if (cmb_last_bgzf_batch(ctx_, &again, &nr, &ni) != CMB_OK) break;

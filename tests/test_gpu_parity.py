@@ -156,6 +156,24 @@ def test_host_decode_path_matches_oracle(synth, which, argv):
     assert any(l.startswith("#pipeline") for l in g.stderr.splitlines())
 
 
+INFLATE_MODES = [(k, m) for k in ("t1", "g8", "w1") for m in ("persistent", "serial")] + [("t1", "windows")]
+
+
+@pytest.mark.parametrize("kernel,mode", INFLATE_MODES, ids=[f"{k}-{m}" for k, m in INFLATE_MODES])
+def test_every_inflate_kernel_and_launch_mode_matches_zlib(synth, kernel, mode):
+    """The three inflate kernels (thread / eight lanes / warp per block) under the three launch disciplines: one persistent launch
+    whose lanes wait for their window's arrival flag (64 KB windows here, so that a small file spans many), one launch ordered
+    behind all the copies (what runs under ncu / compute-sanitizer and for single-window files), one launch per window."""
+    env = {"CMB_PIPELINE_STATS": "1", "CMB_DECODE_VERIFY": "1", "CMB_INFLATE": kernel, "CMB_DECODE_WINDOW_KB": "64",
+           "CMB_INFLATE_SERIAL": "1" if mode == "serial" else "0", "CMB_INFLATE_WINDOWS": "1" if mode == "windows" else "0"}
+    for which in ("small", "mags"):
+        g = _assert_same(["contig", "-m", "mean", "trimmed_mean", "count", "-b", synth[which]], env=env)
+        st = _decode_stats(g)
+        assert any(l.startswith("#device_decode\tblocks=") and ("host_blocks=0" in l or "host_blocks=1\t" in l) for l in st), st
+        assert any(l.startswith("#decode_verify\t0 of ") for l in st), st
+        assert not any(l.startswith("#decode_status") and "\t31:" in l for l in st), st  # no window wait expired
+
+
 def test_declined_blocks_get_a_second_device_pass(synth):
     """Blocks the four-streams-per-warp kernel declines are retried with the one-stream-per-warp kernel (larger tables)
     before the host's zlib is asked; CMB_DECODE_RETRY_TEST marks every 7th block as declined to exercise that path."""
