@@ -60,11 +60,7 @@ struct InflateArgs {
   // (written by the copy stream after the window's bytes; NULL = everything is resident)
   const uint32_t* block_window;
   const uint32_t* ready;
-  // kd_inflate_t1 claims blocks in file order as their windows arrive: win_b0[w] = first block of window w
-  // (win_b0[n_windows] = b1), *wm = number of leading windows known to have arrived (zeroed by the host)
-  const uint32_t* win_b0;
-  uint32_t* wm;
-  uint32_t n_windows;
+  uint32_t lane_limit;  // kd_inflate_t1: lanes per warp that take blocks (0 = all 32)
   // optional indirection: ticket t in [b0, b1) names block block_list[t] (second pass over the blocks the first declined)
   const uint32_t* block_list;
   uint8_t* scratch;  // kd_inflate_t1: 160 bytes per BGZF block (indexed by block number)

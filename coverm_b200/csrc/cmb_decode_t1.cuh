@@ -126,14 +126,10 @@ __device__ __forceinline__ unsigned long long t1_now_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-__device__ __forceinline__ uint32_t t1_lane_busy(volatile uint32_t* w, int d) { return atomicAdd(const_cast<uint32_t*>(w), (uint32_t)d); }
+__device__ __forceinline__ void t1_lane_busy(volatile uint32_t* w, int d) { atomicAdd(const_cast<uint32_t*>(w), (uint32_t)d); }
 #else
 static inline unsigned long long t1_now_ns() { return 0; }
-static inline uint32_t t1_lane_busy(volatile uint32_t* w, int d) { const uint32_t o = *w; *w += (uint32_t)d; return o; }
-static inline uint32_t atomicCAS(uint32_t* p, uint32_t c, uint32_t v) { const uint32_t o = *p; if (o == c) *p = v; return o; }
-static inline uint32_t atomicMax(uint32_t* p, uint32_t v) { const uint32_t o = *p; if (v > o) *p = v; return o; }
-static inline void __threadfence() {}
-using std::max;
+static inline void t1_lane_busy(volatile uint32_t* w, int d) { *w += (uint32_t)d; }
 static inline void __syncwarp() {}
 #endif
 __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs a) {
@@ -162,13 +158,13 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
       pm_len = 0;
     }
   };
-  enum : uint32_t { IDLE, HDR, SYM, FIN };
+  enum : uint32_t { IDLE, WAIT, HDR, SYM, FIN };
   uint32_t state = IDLE;
   uint32_t b = 0, n_out = 0, op = 0, bfinal = 0, spins = 0, skip = 0;
   unsigned long long wait_t0 = 0;
-  // Lanes of one warp are in different states.  An idle lane must not hold up the lanes that are decoding (every trip round
-  // this loop is one symbol for them), so it sleeps only while NO lane of its warp holds a block (t1_busy counts those) and
-  // otherwise just looks again some iterations later.
+  // Lanes of one warp are in different states.  A lane whose window has not arrived must not hold up the lanes that are
+  // decoding (every trip round this loop is one symbol for them), so it sleeps only while NO lane of its warp decodes
+  // (t1_busy counts those) and otherwise just looks at the flag again some iterations later.
   __shared__ uint32_t t1_busy[T1_THREADS / 32];
   volatile uint32_t* const my_busy = t1_busy + (threadIdx.x >> 5);
   if ((threadIdx.x & 31) == 0) *my_busy = 0;
@@ -177,79 +173,55 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
   const uint8_t* in_end = nullptr;
   uint8_t* out = nullptr;
 
-  const uint32_t n_tickets = a.b1 - a.b0;
-  const uint32_t n_warps = max(1u, (uint32_t)gridDim.x * (T1_THREADS / 32));
+  // A warp's lanes are in different states most of the time, so a block takes the longer the more lanes of its warp hold one.
+  // With fewer blocks than the grid has lanes, only the first lane_limit lanes of every warp work: the blocks spread over all
+  // the warps instead of filling the first ones.
+  if (a.lane_limit && (threadIdx.x & 31) >= a.lane_limit) return;
   for (;;) {
     // ------------------------------------------------------------------ a new block
-    // A warp works its lanes' blocks off one after the other (the lanes are in different states all the time), so what counts
-    // is how many blocks a WARP holds: one block per warp is decoded in ~2 ms, thirty-two take sixty.  Blocks are therefore
-    // claimed one at a time, only once their window has arrived, and a lane claims only while its warp holds fewer blocks
-    // than its fair share of the backlog (arrived, unclaimed blocks / warps of the grid): with the file already resident that
-    // spreads the blocks evenly over every warp; while the file is still arriving the backlog stays short, every warp holds
-    // a block or two and the last window is done a few ms after it came in.
-    if (state == IDLE && skip) {
+    if (state == IDLE) {
+      const uint32_t tk = atomicAdd(a.ticket, 1u);
+      if (tk >= a.b1 - a.b0) return;
+      b = a.block_list ? a.block_list[tk] : a.b0 + tk;
+      spins = 0;
+      skip = 0;
+      wait_t0 = 0;
+      state = WAIT;
+    }
+    if (state == WAIT && skip) {
       --skip;
-    } else if (state == IDLE) {
-      const uint32_t tk = *(volatile uint32_t*)a.ticket;
-      if (tk >= n_tickets) return;
-      uint32_t avail = n_tickets;
-      if (a.ready) {  // the windows arrive roughly in order: a.wm = number of leading windows that are in
-        const uint32_t w0 = *(volatile uint32_t*)a.wm;
-        uint32_t w = w0;
-        while (w < a.n_windows && *(const volatile uint32_t*)(a.ready + w) != 0) ++w;
-        if (w > w0) {
-          __threadfence();
-          atomicMax(a.wm, w);
-        }
-        const uint32_t wb = a.win_b0[w];  // first block of the first window still missing (win_b0[n_windows] = b1)
-        avail = (wb < a.b1 ? wb : a.b1) - a.b0;
-      }
-      bool claimed = false;
-      if (tk < avail) {
-        const uint32_t backlog = avail - tk;
-        const uint32_t quota = (backlog + n_warps - 1) / n_warps;
-        const uint32_t held = t1_lane_busy(my_busy, 1);
-        if (held < quota && atomicCAS(a.ticket, tk, tk + 1u) == tk) {
-          claimed = true;
-          counted = true;
-        } else {
-          t1_lane_busy(my_busy, -1);
-        }
-      }
-      if (claimed) {
-        __threadfence();  // the window's bytes were written (by the copy engine) before its flag
-        b = a.block_list ? a.block_list[tk] : a.b0 + tk;
-        spins = 0;
-        wait_t0 = 0;
+    } else if (state == WAIT) {
+      bool arrived = true;
+      if (a.ready) arrived = *(const volatile uint32_t*)(a.ready + a.block_window[b]) != 0;
+      if (arrived) {
+        if (a.ready) __threadfence_system();  // the flag was written by the copy engine after the window's bytes
         n_out = a.isize[b];
         const uint8_t* in = a.comp + a.coff[b];
         in_end = in + a.clen[b];
         out = a.out + a.uoff[b];
         op = 0;
         if (n_out == 0) {
-          a.status[b] = 0;  // state stays IDLE; the lane's hold on its warp is released at the end of this trip
+          a.status[b] = 0;
+          state = IDLE;
         } else {
           br.init(in);
           state = HDR;
+          t1_lane_busy(my_busy, 1);
+          counted = true;
         }
-      } else if (tk >= avail && a.ready) {  // nothing to claim because nothing more has arrived
+      } else {
         const unsigned long long now = t1_now_ns();
         if (wait_t0 == 0) wait_t0 = now;
-        if (now - wait_t0 > T1_WAIT_NS) {
-          // the next window never came (copy failure, a tool serialising the streams): give the remaining blocks back
-          // (status 31: the host inflates them), every lane helping
-          const uint32_t t2 = atomicAdd(a.ticket, 1u);
-          if (t2 >= n_tickets) return;
-          a.status[a.b0 + t2] = 31u;
+        if (now - wait_t0 > T1_WAIT_NS) {  // the window never came (copy failure, a tool serialising the streams)
+          a.status[b] = 31u;
           atomicAdd(a.fail_count, 1u);
-        } else if (*my_busy == 0) {  // the whole warp is idle: back off, 0.25 .. 8 us, to keep the polls off the L2
-          __nanosleep(256u << (spins < 5u ? spins : 5u));
+          state = IDLE;
+        } else if (*my_busy == 0) {  // the whole warp waits: back off, 0.25 .. 4 us, to keep the polls off the L2
+          __nanosleep(256u << (spins < 4u ? spins : 4u));
           ++spins;
         } else {
           skip = 64;  // other lanes are decoding: no sleeping, look again 64 symbols later
         }
-      } else if (*my_busy != 0) {
-        skip = 16;  // the warp holds its share (or another lane won the ticket)
       }
     }
     uint32_t st = 0;  // the check that declined the block, 0 = fine

@@ -1178,9 +1178,17 @@ int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first
   const uint32_t nb = a.b1 - a.b0;
   if (k == 0) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
-    uint32_t grid = std::min<uint32_t>((nb + T1_THREADS - 1) / T1_THREADS, (uint32_t)c->sm_count * 5);
+    // every resident warp takes part; with fewer blocks than lanes, each warp works with its first `lanes` lanes only
+    const uint32_t max_grid = (uint32_t)c->sm_count * 5, warps = max_grid * (T1_THREADS / 32);
+    uint32_t lanes = std::min<uint32_t>(32, std::max<uint32_t>(1, (nb + warps - 1) / warps));
+    static const int lanes_forced = [] { const char* e = getenv("CMB_T1_LANES"); return e ? atoi(e) : 0; }();  // experiment knob
+    if (lanes_forced > 0) lanes = std::min<uint32_t>(32, (uint32_t)lanes_forced);
+    const uint32_t per_cta = lanes * (T1_THREADS / 32);
+    uint32_t grid = std::min<uint32_t>((nb + per_cta - 1) / per_cta, max_grid);
     if (const char* cap = getenv("CMB_T1_MAX_CTAS")) grid = std::max<uint32_t>(1, std::min<uint32_t>(grid, (uint32_t)atoi(cap)));  // experiment knob: fewer live streams
-    kd_inflate_t1<<<grid, T1_THREADS, T1_SMEM_BYTES, st>>>(a);
+    InflateArgs at = a;
+    at.lane_limit = lanes;
+    kd_inflate_t1<<<grid, T1_THREADS, T1_SMEM_BYTES, st>>>(at);
     CU_TRY(c, cudaGetLastError());
     if (crc_pending) *crc_pending = true;
     else if (int rc = launch_crc32(c, a, st)) return rc;
@@ -1415,8 +1423,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
       byte0 = byte1;
     }
   }
-  // [0] block ticket, [1, 1 + W) arrival flags, [1 + W] watermark, [2 + W, 3 + 2W] first block of each window
-  if (d.tickets_cap < 2 * windows.size() + 8 || !d.d_tickets) {
+  if (d.tickets_cap < windows.size() + 8 || !d.d_tickets) {  // [0] block ticket, [1, 1 + W) arrival flags
     cudaFree(d.d_tickets);
     d.d_tickets = nullptr;
     d.tickets_cap = 0;
@@ -1462,7 +1469,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
   CU_TRY(c, cudaMemsetAsync(d.d_cnt, 0, 64, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_status, 0, 4ull * nb, c->stream));
   CU_TRY(c, cudaMemcpyAsync(d.d_block_window, block_window.data(), 4ull * nb, cudaMemcpyHostToDevice, c->stream));
-  CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * (windows.size() + 2), c->stream));  // ticket, arrival flags, watermark
+  CU_TRY(c, cudaMemsetAsync(d.d_tickets, 0, 4 * (windows.size() + 1), c->stream));
   CU_TRY(c, cudaMemsetAsync(infl_base + total, 0, DEC_SLACK, c->stream));
   CU_TRY(c, cudaMemsetAsync(comp_base + byte_hi, 0, DEC_SLACK, c->stream));
   CU_TRY(c, cudaMemsetAsync(d.d_comp, 0, DEC_FRONT, c->stream));
@@ -1473,7 +1480,6 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
   const uint32_t NCS = 64;  // compute streams for the per-window launches
   bool crc_pending = false;
   InflateArgs persistent_args{};
-  std::vector<uint32_t> win_b0;  // outlives the asynchronous upload (pageable source: staged at the call)
   if (per_window) {
     CU_TRY(c, cudaFuncSetAttribute(kd_inflate_t1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)T1_SMEM_BYTES));
     while (d.cstreams.size() < std::min<size_t>(NCS, windows.size())) {
@@ -1496,13 +1502,6 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     // blocks before the one holding the first record are header text the host has already read: not inflated here
     a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
     a.block_window = d.d_block_window; a.ready = d.d_tickets + 1;
-    a.wm = d.d_tickets + 1 + windows.size(); a.win_b0 = d.d_tickets + 2 + windows.size(); a.n_windows = (uint32_t)windows.size();
-    {
-      win_b0.resize(windows.size() + 1);
-      for (size_t w = 0; w < windows.size(); ++w) win_b0[w] = windows[w].b0;
-      win_b0[windows.size()] = data_end;
-      CU_TRY(c, cudaMemcpyAsync(d.d_tickets + 2 + windows.size(), win_b0.data(), 4 * win_b0.size(), cudaMemcpyHostToDevice, c->stream));
-    }
     if (getenv("CMB_PREWARM")) {  // experiment: every copy stream has executed something before the persistent kernel starts
       for (uint32_t t = 0; t < T; ++t) {
         CU_TRY(c, cudaMemcpyAsync(d.d_cnt + 12, d.h_ones, 4, cudaMemcpyHostToDevice, d.streams[t]));

@@ -613,7 +613,23 @@ class DeviceSession {
           try {
             BlockRangeFinder finder(bx, n_ref, records_at);
             const bool last = group_rank_ == group_n_ - 1;
-            const BlockRange br = finder.find(sb, se, group_rank_ == 0, last);
+            // reads cover the reference roughly evenly, so a tid's records start near its share of the summed contig length
+            double frac_lo = -1.0, frac_hi = -1.0;
+            {
+              long double before_lo = 0, before_hi = 0, total = 0;
+              const auto& lens = res.hdr->lens;
+              for (size_t t = 0; t < lens.size(); ++t) {
+                if (t == sb) before_lo = total;
+                if (t == se) before_hi = total;
+                total += (long double)lens[t];
+              }
+              if (se >= lens.size()) before_hi = total;
+              if (total > 0) {
+                frac_lo = (double)(before_lo / total);
+                frac_hi = (double)(before_hi / total);
+              }
+            }
+            const BlockRange br = finder.find(sb, se, group_rank_ == 0, last, frac_lo, frac_hi);
             bi.ranged = 1;
             bi.walk_begin_block = br.walk_begin;
             bi.walk_end_block = br.walk_end;

@@ -12,6 +12,7 @@
 #pragma once
 #include <algorithm>
 #include <cstdint>
+#include <utility>
 #include <vector>
 
 #include "decode_pipeline.hpp"
@@ -52,7 +53,14 @@ class BlockRangeFinder {
 
   // Range of rank `rank`: tids [t_lo, t_hi); `last` = this rank also takes the unplaced tail (tid < 0) and runs to the end.
   // Throws Panic on a stream whose record boundaries cannot be established (the caller then decodes the whole file).
-  BlockRange find(uint32_t t_lo, uint32_t t_hi, bool first_rank, bool last) {
+  // frac_lo / frac_hi (optional, in [0, 1]): where the records of t_lo / t_hi are expected to start as a fraction of the record
+  // stream -- the caller's cumulative contig length is a good guess when reads cover the reference evenly.  A hint only
+  // changes WHERE the search starts (galloping from the guess before bisecting), never its result.
+  BlockRange find(uint32_t t_lo, uint32_t t_hi, bool first_rank, bool last, double frac_lo = -1.0, double frac_hi = -1.0) {
+    hint_lo_ = frac_lo;
+    hint_hi_ = frac_hi;
+    t_lo_ = t_lo;
+    t_hi_ = t_hi;
     BlockRange r;
     if (first_rank || t_lo == 0) {
       r.walk_begin = first_;
@@ -140,12 +148,47 @@ class BlockRangeFinder {
 
   // Smallest block b in [first_, nb_] with key(b) >= t  (every record with a smaller tid starts before block b's first record).
   uint32_t lower_bound_block(uint32_t t) {
+    if (bound_cached_[0].first == (int64_t)t) return bound_cached_[0].second;
+    if (bound_cached_[1].first == (int64_t)t) return bound_cached_[1].second;
     uint32_t lo = first_, hi = nb_;
+    // invariant: the answer lies in [lo, hi]; key(hi) >= t or hi == nb_; key(b) < t for every b < lo
+    const double frac = t == t_lo_ ? hint_lo_ : t == t_hi_ ? hint_hi_ : -1.0;
+    if (frac >= 0.0 && frac <= 1.0 && nb_ - first_ > 64) {
+      uint32_t g = first_ + (uint32_t)(frac * (double)(nb_ - first_));
+      if (g >= nb_) g = nb_ - 1;
+      uint32_t step = 8;
+      if (key_at_or_after(g) >= (int64_t)t) {  // the answer is at or before g: gallop backwards
+        hi = g;
+        while (hi > lo) {
+          const uint32_t p = hi - lo > step ? hi - step : lo;
+          if (key_at_or_after(p) >= (int64_t)t) {
+            hi = p;
+            step *= 4;
+          } else {
+            lo = p + 1;
+            break;
+          }
+        }
+      } else {  // after g: gallop forwards
+        lo = g + 1;
+        while (lo < hi) {
+          const uint32_t p = hi - lo > step ? lo + step : hi;
+          if (p >= hi) break;
+          if (key_at_or_after(p) >= (int64_t)t) {
+            hi = p;
+            break;
+          }
+          lo = p + 1;
+          step *= 4;
+        }
+      }
+    }
     while (lo < hi) {
       const uint32_t mid = lo + (hi - lo) / 2;
       if (key_at_or_after(mid) >= (int64_t)t) hi = mid;
       else lo = mid + 1;
     }
+    bound_cached_[bound_cached_[0].first < 0 ? 0 : 1] = {(int64_t)t, lo};
     return lo;
   }
 
@@ -205,6 +248,9 @@ class BlockRangeFinder {
   };
   const BlockIndex& bx_;
   uint32_t n_ref_, nb_ = 0, first_ = 0, probes_ = 0;
+  uint32_t t_lo_ = 0, t_hi_ = 0;
+  double hint_lo_ = -1.0, hint_hi_ = -1.0;
+  std::pair<int64_t, uint32_t> bound_cached_[2] = {{-1, 0}, {-1, 0}};  // lower_bound_block results of this find()
   uint64_t records_at_;
   BgzfInflater inf_;
   std::vector<uint8_t> buf_;
