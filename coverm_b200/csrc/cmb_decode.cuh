@@ -60,7 +60,8 @@ struct InflateArgs {
   // (written by the copy stream after the window's bytes; NULL = everything is resident)
   const uint32_t* block_window;
   const uint32_t* ready;
-  uint32_t lane_limit;  // kd_inflate_t1: lanes per warp that take blocks (0 = all 32)
+  uint32_t lane_limit;    // kd_inflate_t1: lanes per warp that take blocks (0 = all 32)
+  uint32_t static_first;  // kd_inflate_t1: the first block of every lane is dealt out column-wise (see the kernel)
   // optional indirection: ticket t in [b0, b1) names block block_list[t] (second pass over the blocks the first declined)
   const uint32_t* block_list;
   uint8_t* scratch;  // kd_inflate_t1: 160 bytes per BGZF block (indexed by block number)

@@ -177,10 +177,25 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
   // With fewer blocks than the grid has lanes, only the first lane_limit lanes of every warp work: the blocks spread over all
   // the warps instead of filling the first ones.
   if (a.lane_limit && (threadIdx.x & 31) >= a.lane_limit) return;
+  // While the file is still arriving, which blocks a warp holds decides when it works: with tickets in launch order a warp's
+  // lanes hold NEIGHBOURING blocks, sit idle until their window is in and then decode all at once -- the warps holding the
+  // end of the file start last and the whole call ends a full block latency (tens of ms) after the last byte arrived.  The
+  // first round is therefore dealt out column-wise (static_first): a warp's lanes hold blocks spread evenly over the file, so
+  // at any moment one or two of its lanes decode and the last window's blocks are alone in their warps.  Later rounds (more
+  // blocks than lanes) take tickets in file order.
+  const uint32_t n_warps = gridDim.x * (T1_THREADS / 32);
+  bool first_round = a.static_first != 0;
+  const uint32_t static_round = first_round ? (a.lane_limit ? a.lane_limit : 32u) * n_warps : 0u;
   for (;;) {
     // ------------------------------------------------------------------ a new block
     if (state == IDLE) {
-      const uint32_t tk = atomicAdd(a.ticket, 1u);
+      uint32_t tk;
+      if (first_round) {  // lane j of warp w starts with block j * n_warps + w: one block of every stretch of the file per warp
+        tk = (threadIdx.x & 31) * n_warps + (blockIdx.x * (T1_THREADS / 32) + (threadIdx.x >> 5));
+        first_round = false;
+      } else {
+        tk = static_round + atomicAdd(a.ticket, 1u);
+      }
       if (tk >= a.b1 - a.b0) return;
       b = a.block_list ? a.block_list[tk] : a.b0 + tk;
       spins = 0;
@@ -220,7 +235,7 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
           __nanosleep(256u << (spins < 4u ? spins : 4u));
           ++spins;
         } else {
-          skip = 64;  // other lanes are decoding: no sleeping, look again 64 symbols later
+          skip = 512;  // other lanes are decoding: no sleeping, look again 512 symbols later
         }
       }
     }

@@ -1188,6 +1188,8 @@ int launch_inflate(cmb_ctx* c, const InflateArgs& a, cudaStream_t st, bool first
     if (const char* cap = getenv("CMB_T1_MAX_CTAS")) grid = std::max<uint32_t>(1, std::min<uint32_t>(grid, (uint32_t)atoi(cap)));  // experiment knob: fewer live streams
     InflateArgs at = a;
     at.lane_limit = lanes;
+    static const bool in_order = getenv("CMB_T1_IN_ORDER") && getenv("CMB_T1_IN_ORDER")[0] == '1';  // experiment knob
+    at.static_first = (!a.block_list && !in_order) ? 1u : 0u;
     kd_inflate_t1<<<grid, T1_THREADS, T1_SMEM_BYTES, st>>>(at);
     CU_TRY(c, cudaGetLastError());
     if (crc_pending) *crc_pending = true;
