@@ -177,12 +177,9 @@ __global__ void __launch_bounds__(T1_THREADS, 5) kd_inflate_t1(const InflateArgs
   // With fewer blocks than the grid has lanes, only the first lane_limit lanes of every warp work: the blocks spread over all
   // the warps instead of filling the first ones.
   if (a.lane_limit && (threadIdx.x & 31) >= a.lane_limit) return;
-  // While the file is still arriving, which blocks a warp holds decides when it works: with tickets in launch order a warp's
-  // lanes hold NEIGHBOURING blocks, sit idle until their window is in and then decode all at once -- the warps holding the
-  // end of the file start last and the whole call ends a full block latency (tens of ms) after the last byte arrived.  The
-  // first round is therefore dealt out column-wise (static_first): a warp's lanes hold blocks spread evenly over the file, so
-  // at any moment one or two of its lanes decode and the last window's blocks are alone in their warps.  Later rounds (more
-  // blocks than lanes) take tickets in file order.
+  // static_first (experiment, off by default): the first round is dealt out column-wise -- lane j of warp w starts with block
+  // j * n_warps + w, so a warp's lanes hold blocks spread evenly over the file instead of neighbouring ones.  Measured: no
+  // shorter tail on a streamed file, slower on a resident one (the neighbours' locality is lost).
   const uint32_t n_warps = gridDim.x * (T1_THREADS / 32);
   bool first_round = a.static_first != 0;
   const uint32_t static_round = first_round ? (a.lane_limit ? a.lane_limit : 32u) * n_warps : 0u;
