@@ -44,6 +44,8 @@
 #include <vector>
 
 #include <nccl.h>
+#include <strings.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include "../../include/coverm_b200.h"
@@ -939,11 +941,33 @@ namespace {
 // NCCL writes its banner / debug lines to stdout by default; stdout carries the coverage table.
 void nccl_output_to_stderr() {
   static const bool once = [] {
+    // NCCL honours NCCL_DEBUG_FILE only above the VERSION level: at NCCL_DEBUG=VERSION the banner goes to stdout regardless
+    const char* lvl = getenv("NCCL_DEBUG");
+    if (lvl && !strcasecmp(lvl, "VERSION")) setenv("NCCL_DEBUG", "WARN", 1);  // WARN prints the same banner, to the debug file
     if (!getenv("NCCL_DEBUG_FILE")) setenv("NCCL_DEBUG_FILE", "/dev/stderr", 0);
     return true;
   }();
   (void)once;
 }
+// While a communicator is created, file descriptor 1 points at stderr: whatever NCCL (or a plugin it loads) prints during
+// initialisation cannot end up in the coverage table.  Nothing else writes to stdout at that point (tables are printed at the end).
+struct StdoutGuard {
+  static std::mutex& mu() { static std::mutex m; return m; }
+  std::lock_guard<std::mutex> lock{mu()};
+  int saved = -1;
+  StdoutGuard() {
+    fflush(stdout);
+    saved = dup(1);
+    if (saved >= 0) dup2(2, 1);
+  }
+  ~StdoutGuard() {
+    fflush(stdout);
+    if (saved >= 0) {
+      dup2(saved, 1);
+      close(saved);
+    }
+  }
+};
 }  // namespace
 
 int cmb_comm_unique_id(uint8_t id[CMB_COMM_ID_BYTES]) {
@@ -951,6 +975,7 @@ int cmb_comm_unique_id(uint8_t id[CMB_COMM_ID_BYTES]) {
   static_assert(sizeof(ncclUniqueId) == CMB_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
   if (!id) return fail(nullptr, CMB_E_ARG, "cmb_comm_unique_id: null argument");
   ncclUniqueId u;
+  StdoutGuard guard;
   NCCL_TRY(nullptr, ncclGetUniqueId(&u));
   memcpy(id, &u, sizeof u);
   return CMB_OK;
@@ -963,7 +988,10 @@ int cmb_comm_init(cmb_ctx* c, const uint8_t id[CMB_COMM_ID_BYTES], int rank, int
   CU_TRY(c, cudaSetDevice(c->device));
   ncclUniqueId u;
   memcpy(&u, id, sizeof u);
-  NCCL_TRY(c, ncclCommInitRank(&c->comm, n_ranks, u, rank));
+  {
+    StdoutGuard guard;
+    NCCL_TRY(c, ncclCommInitRank(&c->comm, n_ranks, u, rank));
+  }
   c->comm_rank = rank;
   c->comm_size = n_ranks;
   return CMB_OK;
@@ -978,7 +1006,10 @@ int cmb_comm_init_local(cmb_ctx* const* ctxs, int n_ranks) {
   }
   std::vector<ncclComm_t> comms(n_ranks);
   nccl_output_to_stderr();
-  NCCL_TRY(ctxs[0], ncclCommInitAll(comms.data(), n_ranks, devs.data()));
+  {
+    StdoutGuard guard;
+    NCCL_TRY(ctxs[0], ncclCommInitAll(comms.data(), n_ranks, devs.data()));
+  }
   auto barrier = std::make_shared<LocalBarrier>();
   barrier->n = n_ranks;
   for (int r = 0; r < n_ranks; ++r) {
