@@ -431,12 +431,13 @@ __global__ void __launch_bounds__(INF_WARPS * 32, 2) kd_inflate(const InflateArg
       uint32_t spins = 0;
       unsigned long long waited_ns = 0;
       while (*flag == 0 && waited_ns < 4000000000ull) {  // bounded (4 s): a copy that never lands must not hang the GPU
-        const uint32_t ns = 256u << min(spins, 7u);      // back-off: see kd_inflate_t1
+        const uint32_t ns = 256u << min(spins, 4u);      // 0.25 .. 4 us back-off; the warp has nothing else to do
         __nanosleep(ns);
         waited_ns += ns;
         ++spins;
       }
       arrived = __all_sync(FULL, *flag != 0);
+      __threadfence_system();  // order the payload reads behind the flag (written by the copy engine after the window's bytes)
     }
     const uint32_t n_out = a.isize[b];
     uint32_t st = arrived ? INF_OK : 31u;

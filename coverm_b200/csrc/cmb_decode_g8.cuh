@@ -291,13 +291,14 @@ __global__ void __launch_bounds__(G8_WARPS * 32, 2) kd_inflate_g8(const InflateA
       uint32_t spins = 0;
       arrived = !have || *flag != 0;
       unsigned long long waited_ns = 0;
-      while (!__all_sync(FULL, arrived) && waited_ns < 2000000000ull) {  // back-off: polling must not crowd out the copy engine's writes
-        const uint32_t ns = 256u << min(spins, 7u);
+      while (!__all_sync(FULL, arrived) && waited_ns < 2000000000ull) {  // the whole warp waits (its four blocks start together)
+        const uint32_t ns = 256u << min(spins, 4u);  // 0.25 .. 4 us: keeps the polls off the L2 without adding latency
         __nanosleep(ns);
         waited_ns += ns;
         ++spins;
         arrived = !have || *flag != 0;
       }
+      __threadfence_system();  // the flag was written by the copy engine after the window's bytes: order the payload reads behind it
     }
     const uint32_t n_out = have ? a.isize[b] : 0;
     const bool run = have && arrived && n_out != 0;

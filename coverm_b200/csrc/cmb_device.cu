@@ -1538,12 +1538,6 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     // blocks before the one holding the first record are header text the host has already read: not inflated here
     a.b0 = first_block; a.b1 = data_end; a.out = infl_base; a.status = d.d_status; a.ticket = d.d_tickets; a.fail_count = d.d_cnt + 0;
     a.block_window = d.d_block_window; a.ready = d.d_tickets + 1;
-    if (getenv("CMB_PREWARM")) {  // experiment: every copy stream has executed something before the persistent kernel starts
-      for (uint32_t t = 0; t < T; ++t) {
-        CU_TRY(c, cudaMemcpyAsync(d.d_cnt + 12, d.h_ones, 4, cudaMemcpyHostToDevice, d.streams[t]));
-        CU_TRY(c, cudaStreamSynchronize(d.streams[t]));
-      }
-    }
     persistent_args = a;
     if ((rc = launch_inflate(c, a, c->stream, true, &crc_pending))) return rc;
   }
