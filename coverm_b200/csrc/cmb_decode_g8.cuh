@@ -215,7 +215,9 @@ __device__ bool g8_build_table(G8Smem& S, const uint8_t* lens, uint32_t n, uint1
     }
   }
   __syncwarp();
-  return !over && S.overflow == 0;
+  const bool ok = !over && S.overflow == 0;
+  __syncwarp();  // the next build resets S.overflow: every lane must have read it first (racecheck: WAR between two builds)
+  return ok;
 }
 
 // CRC-32 of a stream's output by its 8 lanes (8 KB slices), combined as in warp_crc32.

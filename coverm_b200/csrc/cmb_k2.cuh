@@ -55,6 +55,19 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
 
   const uint32_t t = threadIdx.x, lane = t & 31, warp = t >> 5;
 
+#if CMB_K2_STATIC
+  // Static schedule: iteration i of CTA b works on chunk b + i * gridDim.x.  Every thread knows its next chunk, so the chunk's
+  // metadata (first / last contig, carry-in) is requested one iteration ahead and the dependent lookups (contig of the span,
+  // its start and length) can start before the tile has even arrived; no ticket atomics, no ticket hand-over through shared memory.
+  auto chunk_of = [&](uint32_t i) -> uint32_t { return blockIdx.x + i * gridDim.x; };
+  auto issue_static = [&](uint32_t s, uint32_t ck) {  // thread 0: start the TMA load of chunk ck into stage s
+    if (ck < a.n_chunks) {
+      const uint32_t bar = smem_u32(full + s);
+      mbar_arrive_expect_tx(bar, CHUNK_BYTES);
+      tma_load_2d(smem_u32(smem + s * CHUNK_BYTES), &tmap, 0, (int32_t)(ck * CHUNK_ROWS), bar);
+    }
+  };
+#endif
   auto issue = [&](uint32_t s) {  // thread 0: claim the next chunk and start its TMA load into stage s
     // The ticket travels with the barrier phase: it is written before the arrive (release) and read by the consumers
     // after their wait (acquire), so a stage may be refilled for the very next iteration (2-stage rings).
@@ -109,7 +122,11 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
     for (uint32_t b = t; b < 2 * HIST_TOTAL; b += K2_THREADS) hist2[b] = 0;
   __syncthreads();
   if (t == 0)
+#if CMB_K2_STATIC
+    for (uint32_t s = 0; s < K2_STAGES; ++s) issue_static(s, chunk_of(s));
+#else
     for (uint32_t s = 0; s < K2_STAGES; ++s) issue(s);
+#endif
   __syncthreads();
 
   constexpr uint32_t UNITS = SPAN / 4;                 // 16-byte units per span
@@ -127,13 +144,52 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
   };
   const uint32_t E = a.excl;
   uint32_t prev_chunk = 0, prev_slots = 0;
+#if CMB_K2_STATIC
+  uint32_t n_cf = 0, n_cl = 0;  // metadata of the NEXT iteration's chunk, requested an iteration ahead
+  int n_cin = 0;
+  if (chunk_of(0) < a.n_chunks) {
+    n_cf = __ldg(a.chunk_first + chunk_of(0));
+    n_cl = __ldg(a.chunk_first + chunk_of(0) + 1);
+    n_cin = __ldg(a.carry_in + chunk_of(0));
+  }
+#endif
   uint32_t it = 0;
 
   for (;; ++it) {
     const uint32_t s = it % K2_STAGES;
+#if CMB_K2_STATIC
+    const uint32_t chunk = chunk_of(it);
+    if (chunk >= a.n_chunks) break;
+    const uint32_t cf = n_cf, cl = n_cl;
+    const int cin = n_cin;
+    {
+      const uint32_t nx = chunk_of(it + 1);
+      if (nx < a.n_chunks) {
+        n_cf = __ldg(a.chunk_first + nx);
+        n_cl = __ldg(a.chunk_first + nx + 1);
+        n_cin = __ldg(a.carry_in + nx);
+      }
+    }
+    // ---- which contig owns this thread's span (needs no tile data: these loads fly while the tile arrives and is scanned)
+    const uint32_t span = chunk * CHUNK_SPANS + t;
+    uint32_t c;
+    {
+      uint32_t lo = cf, hi = cl;
+      while (lo < hi) {
+        const uint32_t mid = (lo + hi + 1) >> 1;
+        if (__ldg(a.off_span + mid) <= span) lo = mid;
+        else hi = mid - 1;
+      }
+      c = lo;
+    }
+    const uint32_t cstart = __ldg(a.off_span + c);
+    const uint32_t L = __ldg(a.len + c);
+    mbar_wait(smem_u32(full + s), (it / K2_STAGES) & 1);
+#else
     mbar_wait(smem_u32(full + s), (it / K2_STAGES) & 1);
     const uint32_t chunk = *(volatile uint32_t*)(s_chunk + s);
     if (chunk >= a.n_chunks) break;
+#endif
     int2* wagg = wagg2 + (it & 1) * K2_WARPS;
     uint32_t* hist = hist2 + (it & 1) * HIST_TOTAL;
 
@@ -143,7 +199,9 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
 #if CMB_K2_COOP && CMB_SPAN == 32
     const uint8_t* rowp = tilep + row * 128;
 #endif
+#if !CMB_K2_STATIC
     const uint32_t span = chunk * CHUNK_SPANS + t;
+#endif
     int total = 0;
     evmask_t ev = 0;
 #if CMB_K2_COOP && CMB_SPAN == 32
@@ -199,6 +257,7 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
 #endif
 
     // ---- which contig owns this span
+#if !CMB_K2_STATIC
     const uint32_t cf = __ldg(a.chunk_first + chunk);
     const uint32_t cl = __ldg(a.chunk_first + chunk + 1);
     uint32_t lo = cf, hi = cl;
@@ -210,6 +269,7 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
     const uint32_t c = lo;
     const uint32_t cstart = __ldg(a.off_span + c);
     const uint32_t L = __ldg(a.len + c);
+#endif
     const bool is_head = span == cstart;
     const uint32_t rel = (span - cstart) * SPAN;  // position in the contig of the span's first element
     const uint32_t n_in = rel >= L ? 0u : min(SPAN, L - rel);
@@ -241,7 +301,11 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
     if (lane == 31) wagg[warp] = make_int2(val, flg);
     __syncthreads();  // warp aggregates visible; the previous iteration's tile and histogram adds are complete
     if (it > 0) {
+#if CMB_K2_STATIC
+      if (t == 0) issue_static((it - 1) % K2_STAGES, chunk_of(it - 1 + K2_STAGES));  // refill the tile of the previous iteration
+#else
       if (t == 0) issue((it - 1) % K2_STAGES);  // refill the tile of the previous iteration (read until this barrier)
+#endif
       if (HIST) flush_hist(hist2 + ((it & 1) ^ 1) * HIST_TOTAL, prev_chunk, prev_slots);
     }
 
@@ -267,7 +331,9 @@ __global__ void __launch_bounds__(K2_THREADS, CMB_K2_MINBLOCKS) k2_scan_reduce(c
         wf = 0;
       }
     }
+#if !CMB_K2_STATIC
     const int cin = __ldg(a.carry_in + chunk);
+#endif
     int carry;
     if (is_head) carry = 0;
     else if (pflg) carry = pval;
