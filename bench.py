@@ -471,7 +471,7 @@ def main():
                                                                      "decode_extract_ms", "shard_blocks", "total_blocks", "range_probes",
                                                                      "tid_begin", "tid_end", "group_ranks"]},
                     "step_walls_s": step_walls, "gpu_launches_per_step": int(e2e_launches),
-                    "decode": "device (kd_inflate_g8/kd_guess/kd_walk/kd_extract: compressed BGZF bytes cross PCIe)" if s0["device_decode"] else "host pipeline (tuples cross PCIe)",
+                    "decode": "device (kd_inflate_t1 or kd_inflate_g8 by block count, kd_guess/kd_walk/kd_extract: compressed BGZF bytes cross PCIe)" if s0["device_decode"] else "host pipeline (tuples cross PCIe)",
                     "input": f"BAM bytes ({len(bam_bytes)} B) in pinned host memory, cmbh_run (== `coverm {cfg['sub']}`), TSV text out; "
                              "warm session (context, arena, decode buffers and the parsed header are reused across steps)" +
                              ("; collective: every rank calls cmbh_run, the in-library NCCL gather is inside the timed region" if strong else ""),

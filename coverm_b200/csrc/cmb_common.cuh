@@ -21,7 +21,7 @@ constexpr uint32_t K2_WARPS = K2_THREADS / 32;  // 16
 #define CMB_K2_COOP 0  // K2 experiment: warp-cooperative handling of the non-empty spans (measured SLOWER: 2.85 vs 2.66 ms on config 2)
 #endif
 #ifndef CMB_K2_STATIC
-#define CMB_K2_STATIC 0  // K2 experiment: static chunk schedule + metadata requested an iteration ahead
+#define CMB_K2_STATIC 1  // K2: static chunk schedule, chunk metadata requested an iteration ahead (0 = dynamic tickets; 2.64 vs 2.69 ms)
 #endif
 #ifndef CMB_HIST_SLOTS
 #define CMB_HIST_SLOTS 8
