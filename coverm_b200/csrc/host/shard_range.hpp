@@ -44,7 +44,9 @@ struct BlockRange {
 
 class BlockRangeFinder {
  public:
-  BlockRangeFinder(const BlockIndex& bx, uint32_t n_ref, uint64_t records_at) : bx_(bx), n_ref_(n_ref), records_at_(records_at) {
+  // hint_min_blocks: files with fewer blocks are bisected even when a hint is given (fewer probes than galloping)
+  BlockRangeFinder(const BlockIndex& bx, uint32_t n_ref, uint64_t records_at, uint32_t hint_min_blocks = 1024)
+      : bx_(bx), n_ref_(n_ref), hint_min_blocks_(hint_min_blocks), records_at_(records_at) {
     nb_ = (uint32_t)bx.blocks.size();
     first_ = (uint32_t)(std::upper_bound(bx.ustart.begin(), bx.ustart.end(), records_at) - bx.ustart.begin()) - 1;
     if (first_ > nb_) first_ = nb_;
@@ -110,18 +112,32 @@ class BlockRangeFinder {
       start = (size_t)(records_at_ - bx_.ustart[b]);  // known exactly
       if (start >= own) start = (size_t)-1;
     } else {
+      // A run of six consistent headers confirms a guess; so does a shorter run that reaches the end of the inflated data.  A
+      // candidate whose FIRST record already points past the data (a very long read -- or four stray bytes that happen to look like
+      // a multi-megabyte block_size in front of the real header, e.g. the tail `NM:C:0` of the previous record) proves nothing
+      // by itself: it is only taken when no other offset of the block yields a checked run.
+      size_t unchecked = (size_t)-1, landed = (size_t)-1;
+      const bool to_eof = e == nb_;
       for (size_t s = 0; s < own && start == (size_t)-1; ++s) {
         if (!record_plausible(buf_.data(), s, usize, n_ref_)) continue;
         size_t q = s;
         int ok = 0;
-        while (ok < 6) {  // a run of six consistent headers (or reaching the end of the data) confirms the guess
-          if (q + 36 > usize) { ok = 6; break; }
+        bool ran_off = false;
+        while (ok < 6) {
+          if (q + 36 > usize) {
+            ran_off = true;
+            break;
+          }
           if (!record_plausible(buf_.data(), q, usize, n_ref_)) break;
           q += 4 + (size_t)rd_u32(buf_.data() + q);
           ++ok;
         }
-        if (ok >= 6) start = s;
+        if (ok >= 6 || (ran_off && ok >= 2)) start = s;
+        else if (ran_off && q == usize && to_eof) start = s;  // its record ends exactly where the file's records end
+        else if (ran_off && q <= usize && landed == (size_t)-1) landed = s;  // the next header would start inside the data
+        else if (ran_off && unchecked == (size_t)-1) unchecked = s;
       }
+      if (start == (size_t)-1) start = landed != (size_t)-1 ? landed : unchecked;
     }
     Probe& c = cache_[b];
     if (start == (size_t)-1 || start + 8 > usize) {
@@ -153,7 +169,7 @@ class BlockRangeFinder {
     uint32_t lo = first_, hi = nb_;
     // invariant: the answer lies in [lo, hi]; key(hi) >= t or hi == nb_; key(b) < t for every b < lo
     const double frac = t == t_lo_ ? hint_lo_ : t == t_hi_ ? hint_hi_ : -1.0;
-    if (frac >= 0.0 && frac <= 1.0 && nb_ - first_ > 64) {
+    if (frac >= 0.0 && frac <= 1.0 && nb_ - first_ > hint_min_blocks_) {
       uint32_t g = first_ + (uint32_t)(frac * (double)(nb_ - first_));
       if (g >= nb_) g = nb_ - 1;
       uint32_t step = 8;
@@ -247,7 +263,7 @@ class BlockRangeFinder {
     uint64_t uoff = 0;
   };
   const BlockIndex& bx_;
-  uint32_t n_ref_, nb_ = 0, first_ = 0, probes_ = 0;
+  uint32_t n_ref_, hint_min_blocks_, nb_ = 0, first_ = 0, probes_ = 0;
   uint32_t t_lo_ = 0, t_hi_ = 0;
   double hint_lo_ = -1.0, hint_hi_ = -1.0;
   std::pair<int64_t, uint32_t> bound_cached_[2] = {{-1, 0}, {-1, 0}};  // lower_bound_block results of this find()
