@@ -186,6 +186,21 @@ def test_group_mode_matches_the_oracle(tmp_path, group_bams, world, emu_bgzf):
         assert sum(x["shard_blocks"] for x in first) >= first[0]["total_blocks"] - 2
 
 
+def test_group_mode_eight_ranks(tmp_path, group_bams):
+    """World size 8 (`coverm --gpus 8`, the driver's 8-GPU scaling run): more ranks than some inputs have contigs or BGZF blocks,
+    so several ranks own nothing -- their (empty) ranges, summaries and gathers must still line up."""
+    runs = [GROUP_RUNS(group_bams)[i] for i in (0, 2, 3, 4, 5)]
+    res = _run_group(tmp_path, 8, runs, env={"CMB_EMU_BGZF": "1"})
+    for i, argv in enumerate(runs):
+        rc, out, rm = _oracle(argv)
+        for r in range(8):
+            got = res[r][i]
+            assert got["status"] == rc, (argv, r, got["err"])
+            assert got["out"] == out, (argv, r)
+            assert got["rm"] == rm, (argv, r, got["rm"], rm)
+            assert got["ranks"] == 8
+
+
 def test_group_mode_errors_are_collective(tmp_path):
     """A failure on any rank (here: a record without NM where the reference calls nm(), an unsorted file) reaches every rank
     as the error the reference raises."""
