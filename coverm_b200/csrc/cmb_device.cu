@@ -44,11 +44,28 @@
 #include <vector>
 
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>
 #include <strings.h>
 #include <unistd.h>
 #include <zlib.h>
 
 #include "../../include/coverm_b200.h"
+
+// NVTX ranges around the entry points and the stages of the device decode (visible in Nsight Systems / `ncu --nvtx`; no-ops
+// without a tool attached: nvtx3 is header-only and resolves its injection library lazily).
+struct NvtxRange {
+  bool open = true;
+  explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+  void end() {
+    if (open) {
+      nvtxRangePop();
+      open = false;
+    }
+  }
+  ~NvtxRange() { end(); }
+  NvtxRange(const NvtxRange&) = delete;
+  NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 namespace {
 #include "cmb_common.cuh"
@@ -487,6 +504,7 @@ int cmb_abi_version(void) { return CMB_ABI_VERSION; }
 const char* cmb_last_error(const cmb_ctx* ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
 
 int cmb_create(const cmb_device_cfg* cfg, cmb_ctx** out) {
+  NvtxRange nvtx_fn("cmb_create");
   if (!cfg || !out) return fail(nullptr, CMB_E_ARG, "cmb_create: null argument");
   *out = nullptr;
   int n_dev = 0;
@@ -743,6 +761,7 @@ int cmb_set_params(cmb_ctx* c, const cmb_params* p, cmb_filter_mode* mode_out) {
 }
 
 int cmb_begin_sample(cmb_ctx* c) {
+  NvtxRange nvtx_fn("cmb_begin_sample");
   if (!c) return CMB_E_ARG;
   if (!c->d_rows || !c->have_params) return fail(c, CMB_E_ARG, "cmb_begin_sample: set_reference and set_params first");
   if (c->in_sample) return fail(c, CMB_E_ARG, "cmb_begin_sample: previous sample not ended");
@@ -795,6 +814,7 @@ int cmb_acquire_batch(cmb_ctx* c, cmb_read_batch* batch) {
 }
 
 int cmb_submit_batch(cmb_ctx* c, uint32_t n_records, uint32_t n_intervals) {
+  NvtxRange nvtx_fn("cmb_submit_batch: H2D + K1");
   if (!c) return CMB_E_ARG;
   if (!c->in_sample || c->n_acquired == 0) return fail(c, CMB_E_ARG, "cmb_submit_batch: no acquired batch");
   if (n_records > c->cfg.batch_records || n_intervals > c->cfg.batch_intervals) return fail(c, CMB_E_ARG, "cmb_submit_batch: batch exceeds capacity");
@@ -830,6 +850,7 @@ int cmb_submit_batch(cmb_ctx* c, uint32_t n_records, uint32_t n_intervals) {
 }
 
 int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* dev, uint32_t n_records, uint32_t n_intervals) {
+  NvtxRange nvtx_fn("cmb_submit_device_batch: K1");
   if (!c || !dev) return fail(c, CMB_E_ARG, "cmb_submit_device_batch: null argument");
   if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_submit_device_batch: no sample in progress");
   if (c->n_local == 0) return CMB_OK;
@@ -841,6 +862,7 @@ int cmb_submit_device_batch(cmb_ctx* c, const cmb_read_batch* dev, uint32_t n_re
 }
 
 int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** dev_stats) {
+  NvtxRange nvtx_fn("cmb_end_sample: K1c K1b K2 K3");
   if (!c) return CMB_E_ARG;
   if (!c->in_sample) return fail(c, CMB_E_ARG, "cmb_end_sample: no sample in progress");
   if (c->n_acquired) return fail(c, CMB_E_ARG, "cmb_end_sample: an acquired batch was not submitted");
@@ -861,6 +883,7 @@ int cmb_end_sample_device(cmb_ctx* c, const cmb_contig_stats** dev_stats) {
 }
 
 int cmb_end_sample(cmb_ctx* c, cmb_contig_stats* stats, cmb_hist_pair* pairs, uint64_t pairs_capacity, uint64_t* n_pairs) {
+  NvtxRange nvtx_fn("cmb_end_sample: kernels + D2H");
   if (!c) return fail(c, CMB_E_ARG, "cmb_end_sample: null argument");
   int rc = cmb_end_sample_device(c, nullptr);
   if (rc) return rc;
@@ -929,6 +952,9 @@ int cmb_get_timing(const cmb_ctx* c, cmb_sample_timing* out) {
 }
 
 void* cmb_stream(cmb_ctx* c) { return c ? (void*)c->stream : nullptr; }
+
+void cmb_nvtx_push(const char* name) { nvtxRangePushA(name ? name : "?"); }
+void cmb_nvtx_pop(void) { nvtxRangePop(); }
 
 // ------------------------------------------------------------------------------------------------ multi-GPU (NCCL)
 #define NCCL_TRY(ctx, expr)                                                                                       \
@@ -1055,6 +1081,7 @@ int cmb_comm_allgather(cmb_ctx* c, const void* send, void* recv, size_t bytes) {
 }
 
 int cmb_allgather_stats(cmb_ctx* c, const uint32_t* tid_cuts, const uint64_t* pair_base, cmb_contig_stats* stats, cmb_hist_pair* pairs) {
+  NvtxRange nvtx_fn("cmb_allgather_stats: NCCL gather");
   if (!c || !tid_cuts) return fail(c, CMB_E_ARG, "cmb_allgather_stats: null argument");
   if (!c->comm) return fail(c, CMB_E_ARG, "cmb_allgather_stats: no communicator (cmb_comm_init first)");
   if (!c->ended || !c->d_rows) return fail(c, CMB_E_ARG, "cmb_allgather_stats: no ended sample");
@@ -1370,6 +1397,7 @@ int bgzf_entry(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out, bool 
 }  // namespace
 namespace {
 int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out, bool decode_only) {
+  NvtxRange nvtx_fn("cmb_submit_bgzf");
   if (!c || !in || !out || !in->data || !in->block_coffset || !in->block_clen || !in->block_isize)
     return fail(c, CMB_E_ARG, "cmb_submit_bgzf: null argument");
   if (!decode_only && !c->in_sample) return fail(c, CMB_E_ARG, "cmb_submit_bgzf: no sample in progress");
@@ -1440,6 +1468,7 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     d.have_events = true;
   }
   (void)dummy_cap;
+  NvtxRange nvtx_copy("bgzf: H2D copy + inflate");
   // ---- windows of whole blocks, ~DEC_WINDOW_BYTES of file each
   struct Window { uint32_t b0, b1; uint64_t byte0, byte1; };
   std::vector<Window> windows;
@@ -1652,6 +1681,8 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     cudaEventDestroy(p0);
     cudaEventDestroy(p1);
   }
+  nvtx_copy.end();
+  NvtxRange nvtx_declined("bgzf: declined blocks (second pass, host zlib)");
   // ---- blocks the device declined: zlib on the host, patched into the inflated stream
   uint32_t h_cnt[16];
   CU_TRY(c, cudaMemcpyAsync(h_cnt, d.d_cnt, 64, cudaMemcpyDeviceToHost, c->stream));
@@ -1745,6 +1776,8 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
     inflateEnd(&zs);
     fprintf(stderr, "#decode_verify\t%u of %u blocks differ from zlib; %u inflated on the host\n", bad, data_end - first_block, out->n_blocks_host);
   }
+  nvtx_declined.end();
+  NvtxRange nvtx_chain("bgzf: record chain (guess, walk, verify, offsets)");
   // ---- record chain
   WalkArgs wa{};
   // The chain is walked over [first_block, walk_hi): one block past the range when there is one, so that the range's last
@@ -1788,6 +1821,8 @@ int submit_bgzf_impl(cmb_ctx* c, const cmb_bgzf_input* in, cmb_bgzf_result* out,
   CU_TRY(c, cudaMemcpyAsync(totals, d.d_cnt + 6, 16, cudaMemcpyDeviceToHost, c->stream));
   CU_TRY(c, cudaStreamSynchronize(c->stream));
   CU_TRY(c, cudaEventRecord(d.ev[3], c->stream));
+  nvtx_chain.end();
+  NvtxRange nvtx_extract("bgzf: extract, mate matching, K1");
   const uint64_t n_rec = totals[0], n_cig = totals[1];
   if (n_rec >= 0xffffff00ull || n_cig >= 0xffffff00ull) return fail(c, CMB_E_DECLINED, "cmb_submit_bgzf: more than 2^32 records or cigar operations");
   out->n_records = n_rec;

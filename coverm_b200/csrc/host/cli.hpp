@@ -401,6 +401,7 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
       session = own.get();
     }
     plan.printer.pool = &session->pool();
+    HostRange nvtx_drivers("host: coverage drivers (samples, estimator replay)");
     const double t_driver0 = now_s();
     DriverIO io{session, plan.params, &res.timings, &res.record_counts, (o.quiet || !output_rank) ? nullptr : &err};
     if (o.sub == "contig") {
@@ -443,6 +444,8 @@ inline CliResult run_cli_rank(const std::vector<std::string>& args, const std::v
         res.reads_mapped = mosdepth_genome_coverage_with_contig_names(inputs, gc, taker, !o.no_zeros, plan.estimators, io);
       }
     }
+    nvtx_drivers.end();
+    HostRange nvtx_print("host: print");
     const double t_print0 = now_s();
     if (output_rank) plan.printer.finalise_printing(taker, *os, res.reads_mapped, plan.columns_to_normalise, plan.rpkm_column, plan.tpm_column);
     os->flush();

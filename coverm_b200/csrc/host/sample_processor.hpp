@@ -12,6 +12,21 @@
 
 namespace cmbh {
 
+// NVTX range of a host-side stage (cmb_nvtx_push / cmb_nvtx_pop of the device library; no-ops without a profiler)
+struct HostRange {
+  bool open = true;
+  explicit HostRange(const char* name) { cmb_nvtx_push(name); }
+  void end() {
+    if (open) {
+      cmb_nvtx_pop();
+      open = false;
+    }
+  }
+  ~HostRange() { end(); }
+  HostRange(const HostRange&) = delete;
+  HostRange& operator=(const HostRange&) = delete;
+};
+
 inline double now_s() {
   return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
 }
@@ -284,6 +299,7 @@ class DeviceSession {
       mine.code = 101;
       snprintf(mine.message, sizeof mine.message, "%s", e.what());
     }
+    HostRange nvtx_gather("host: rank summaries + table gather");
     const double t_g0 = now_s();
     std::vector<RankSummary> all((size_t)group_n_);
     group_allgather(&mine, all.data(), sizeof(RankSummary));
@@ -407,6 +423,8 @@ class DeviceSession {
 
   SampleResult process_local(const InputSpec& in, const cmb_params& params, ShardState* shard) {
     SampleResult res;
+    HostRange nvtx_sample("host: sample");
+    HostRange nvtx_header("host: open + BAM header");
     const double t0 = now_s();
     res.stoit_name = file_stem(in.path);
     ByteSource bytes(in);
@@ -480,6 +498,7 @@ class DeviceSession {
     begin += records_at;
     }
     res.timing.header_s = now_s() - t0;
+    nvtx_header.end();
 
     // ---- device reference + params
     uint32_t sb = std::min<uint32_t>(shard_begin_, n_ref), se = std::min<uint32_t>(shard_end_, n_ref);
@@ -567,6 +586,7 @@ class DeviceSession {
     bool decoded_on_device = false;
     {
       // region-parallel pipeline (decode_runner.hpp): this thread only acquires / submits staging batches
+      HostRange nvtx_index("host: BGZF block index (+ range probes in a group)");
       const double t_index0 = now_s();
       BlockIndex bx;
       if (stream.is_raw()) bx.build(stream.raw_data(), stream.raw_size());
@@ -646,6 +666,7 @@ class DeviceSession {
           }
         }
         cmb_bgzf_result br{};
+        nvtx_index.end();
         const double a = now_s();
         res.timing.index_s = now_s() - t_index0;  // incl. the block table and, in a group, the range probes
         const int r2 = range_ok ? cmb_submit_bgzf(ctx_, &bi, &br) : CMB_E_DECLINED;

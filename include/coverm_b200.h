@@ -326,6 +326,11 @@ int cmb_get_timing(const cmb_ctx* ctx, cmb_sample_timing* out);
 /* cudaStream_t of the context (as void*), for callers that order their own work after it. */
 void* cmb_stream(cmb_ctx* ctx);
 
+/* NVTX range on the calling thread (nvtxRangePushA / nvtxRangePop): lets the host side (header parse, block index, range probes,
+ * estimator replay, printing) show up next to the library's own ranges on a profiler timeline.  No-ops without a tool attached. */
+void cmb_nvtx_push(const char* name);
+void cmb_nvtx_pop(void);
+
 #ifdef __cplusplus
 }
 #endif

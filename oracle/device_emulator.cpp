@@ -562,5 +562,7 @@ int cmb_get_timing(const cmb_ctx* c, cmb_sample_timing* t) {
   return CMB_OK;
 }
 void* cmb_stream(cmb_ctx*) { return nullptr; }
+void cmb_nvtx_push(const char*) {}
+void cmb_nvtx_pop(void) {}
 
 }  // extern "C"
