@@ -334,3 +334,24 @@ def test_histogram_buffer_overflow_grows_and_retries(synth):
     for argv in (["contig", "-m", "mean", "trimmed_mean", "variance", "-b", synth["deep"]], ["contig", "-m", "coverage_histogram", "-b", synth["small"]]):
         g = _assert_same(argv, env={"CMB_TEST_SMALL_HIST": "1", "CMB_PIPELINE_STATS": "1"})
         assert "#capacity_retry" in g.stderr, g.stderr[-600:]
+
+
+def test_arena_beyond_2_pow_32_elements(tmp_path):
+    """The north-star reference (906 000 contigs / 5.0 Gbp: the delta arena holds more than 2^32 elements, so every element index of
+    K1 / K2 / the TMA row coordinate is exercised beyond 32 bits) with 10 M reads, the whole table against the oracle.  `bench.py
+    --config ns` repeats this at 52.6 M reads in every run (`"parity": true`)."""
+    import json
+    p = str(tmp_path / "ns10m.bam")
+    out = subprocess.run([coverm_b200.BAMGEN_BIN, "--out", p, "--threads", "16", "--contigs", "906000", "--reads", "10000000", "--seed", "20260925",
+                          "--median-len", "4000", "--sigma", "0.8", "--min-len", "1000", "--max-len", "2000000"],
+                         check=True, capture_output=True, text=True).stdout
+    info = json.loads(out.strip().splitlines()[-1])
+    assert info["bases"] > 2 ** 32 and info["records"] >= 10_000_000, info
+    try:
+        g, o = _both(["contig", "-m", "mean", "trimmed_mean", "covered_fraction", "variance", "-b", p], threads="16",
+                     env={"CMB_PIPELINE_STATS": "1"})
+        assert g.returncode == o.returncode == 0, g.stderr[-1500:]
+        assert g.stdout == o.stdout
+        assert any(l.startswith("#device_decode\tblocks=") for l in g.stderr.splitlines())  # decoded on the device, not declined
+    finally:
+        os.remove(p)
